@@ -1,0 +1,257 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the golden fixtures.
+Needs a B200: every test is marked gpu."""
+import numpy as np
+import pytest
+
+from oracle import c_oracle
+from tests import reference_vectors as rv
+from tests.conftest import board_from_hex, hex_rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    import visapi_b200
+    e = visapi_b200.Engine(0)
+    yield e
+    e.close()
+
+
+def _pack(grid, colorful=True):
+    from visapi_b200 import pack_occupancy
+    return pack_occupancy(np.asarray(grid)[None], colorful)
+
+
+def _tiles(tl, E=None):
+    from visapi_b200 import pack_tiles
+    return pack_tiles([tl], E)
+
+
+# ------------------------------------------------------------- reference unit vectors
+def test_find_first(eng):
+    assert eng.find_first(0, np.array([3.0, 0.0, 1.0, 0.0])) == 1
+    assert eng.find_first(1, np.array([3.0, 0.0, 1.0, 0.0])) == 2
+    assert eng.find_first(7, np.array([3.0, 0.0, 1.0, 0.0])) == -1
+    assert eng.find_first(0, np.array([])) == -1
+    rng = np.random.default_rng(1)
+    for n in (1, 31, 32, 33, 1000, 70001):
+        hay = rng.integers(1, 5, n).astype(np.int32)
+        assert eng.find_first(0, hay) == -1
+        k = int(rng.integers(0, n))
+        hay[k] = 0
+        assert eng.find_first(0, hay) == k
+        hay[min(n - 1, k + 3)] = 0
+        assert eng.find_first(0, hay) == k
+
+
+def test_ref_lfb_vectors(eng):
+    for board, want in rv.LFB:
+        b = np.array(board)
+        got = eng.lfb(_pack(b), b.shape[1])[0]
+        if want is None:
+            assert tuple(got) == (-1, -1, 0)
+        else:
+            assert (got[0], got[1]) == want
+
+
+def test_ref_valid_moves_vectors(eng):
+    for board, tiles, do_sort, want in rv.VALID_MOVES:
+        tl = rv.sort_tiles(tiles) if do_sort else tiles
+        b = np.array(board)
+        for colorful in (True, False):
+            mask, _ = eng.valid_masks(_pack(b, colorful), b.shape[1], _tiles(tl))
+            assert [t for t, m in zip(tl, mask[0]) if m] == want
+
+
+def test_ref_mask_vector(eng):
+    b = np.array(rv.ACTION_GRID)
+    mask, _ = eng.valid_masks(_pack(b, False), b.shape[1], _tiles(rv.MASK_TILES))
+    assert mask[0].tolist() == rv.MASK_EXPECTED
+
+
+def test_ref_next_turn_vector(eng):
+    from visapi_b200 import unpack_occupancy
+    b = np.array(rv.NEXT_TURN_BOARD)
+    occ, tiles, verdict, lfb = eng.transitions(_pack(b, False), 4, _tiles(rv.NEXT_TURN_TILES), [0])
+    assert verdict[0] == 1
+    assert unpack_occupancy(occ, 4)[0].tolist() == rv.NEXT_TURN_AFTER
+    assert tiles[0].tolist() == [[0, 0], [0, 0]]
+    # the (1, 2) tile does not fit at (1, 3)
+    _, _, verdict, _ = eng.transitions(_pack(b, False), 4, _tiles(rv.NEXT_TURN_TILES), [1])
+    assert verdict[0] == 3
+
+
+def test_ref_eliminate_pair_vectors(eng):
+    for tiles, tile, want in rv.ELIMINATE:
+        # a board wide and tall enough that the tile is always placeable
+        b = np.zeros((10, 10))
+        a = tiles.index(tile)
+        _, out_tiles, verdict, _ = eng.transitions(_pack(b), 10, _tiles(tiles), [a], compact=True)
+        if want is ValueError:
+            assert verdict[0] == 5
+        else:
+            assert verdict[0] == 1
+            got = [tuple(t) for t in out_tiles[0].tolist() if t != [0, 0]]
+            assert got == want
+            assert out_tiles[0].tolist()[len(want):] == [[0, 0]] * (len(tiles) - len(want))
+
+
+# ------------------------------------------------------------- reference-made fixtures
+def test_transitions_golden(eng, golden):
+    from visapi_b200 import pack_occupancy, pack_tiles
+    verd = {"ALL_TILES_USED": 2, "TILE_CANNOT_BE_PLACED": 3, "NO_NEXT_POSITION_TILES_UNUSED": 4}
+    walks = golden("transitions.json")
+    # advance all walks in lock step, batching states of equal shape
+    states = []
+    for w in walks:
+        states.append({"w": w, "grid": np.zeros((w["rows"], w["cols"]), np.uint8),
+                       "tiles": [tuple(t) for t in w["tiles"]], "i": 0, "done": False})
+    n_checked = 0
+    while True:
+        live = [s for s in states if not s["done"]]
+        if not live:
+            break
+        groups = {}
+        for s in live:
+            key = (s["w"]["rows"], s["w"]["cols"], len(s["w"]["tiles"]))
+            groups.setdefault(key, []).append(s)
+        for (rows, cols, E), grp in groups.items():
+            occ = pack_occupancy(np.stack([s["grid"] for s in grp]))
+            tiles = pack_tiles([s["tiles"] for s in grp], E)
+            mask, lfb = eng.valid_masks(occ, cols, tiles)
+            ended = eng.game_ended(occ, cols, tiles)
+            actions = np.zeros(len(grp), np.int32)
+            bad_actions = np.full(len(grp), -1, np.int32)
+            for k, s in enumerate(grp):
+                st = s["w"]["steps"][s["i"]]
+                if st["lfb"] is None:
+                    assert tuple(lfb[k]) == (-1, -1, 0)
+                    continue
+                assert [lfb[k][0], lfb[k][1]] == st["lfb"]
+                assert lfb[k][1] + lfb[k][2] == st["next_occupied_col"]
+                n_live = len(s["tiles"])
+                assert mask[k][:n_live].tolist() == st["legal"]
+                assert not mask[k][n_live:].any()
+                assert (ended[k] == 0) == (any(st["legal"]))
+                if "bad_tile" in st:
+                    bad_actions[k] = s["tiles"].index(tuple(st["bad_tile"]))
+                if "pick" in st:
+                    legal_idx = [i for i, f in enumerate(st["legal"]) if f]
+                    actions[k] = legal_idx[st["pick"]]
+            _, _, bad_v, _ = eng.transitions(occ, cols, tiles, bad_actions, want_state=False)
+            out_occ, out_tiles, verdict, _ = eng.transitions(occ, cols, tiles, actions, compact=True)
+            from visapi_b200 import unpack_occupancy
+            grids = unpack_occupancy(out_occ, cols)
+            for k, s in enumerate(grp):
+                st = s["w"]["steps"][s["i"]]
+                n_checked += 1
+                if st["lfb"] is None:
+                    assert verdict[k] == verd[st["verdict"]]
+                    s["done"] = True
+                    continue
+                if "bad_tile" in st:
+                    assert bad_v[k] == verd[st["bad_verdict"]]
+                if "pick" not in st:
+                    assert verdict[k] == 3          # entry 0 is not placeable either
+                    s["done"] = True
+                    continue
+                assert verdict[k] == 1
+                assert hex_rows_of(grids[k]) == st["board_after"]
+                new_tiles = [tuple(t) for t in out_tiles[k].tolist() if t != [0, 0]]
+                assert new_tiles == c_oracle.eliminate_pair(s["tiles"], tuple(st["tile"]))
+                s["grid"], s["tiles"] = grids[k], new_tiles
+                s["i"] += 1
+    assert n_checked > 1000
+
+
+def test_rollouts_golden(eng, golden):
+    from visapi_b200 import pack_occupancy, pack_tiles
+    for case in golden("rollouts.json"):
+        rows, cols = case["rows"], case["cols"]
+        grid = board_from_hex(rows, cols, case.get("board"))
+        tiles = pack_tiles([case["tiles"]])
+        steps, solved, moves = eng.rollouts(
+            pack_occupancy(grid[None]), cols, tiles, n_sims=1, seed=case["seed"],
+            streams=[case["stream"]], tags=[case["tag"]], sim_begin=case["sim"], want_moves=True)
+        assert bool(solved[0, 0]) == case["solved"]
+        assert int(steps[0, 0]) == case["placements"]
+        if not case["solved"]:
+            assert int(steps[0, 0]) == case["depth"]
+        assert moves[0, 0, :steps[0, 0]].tolist() == case["moves"]
+
+
+def test_rollouts_vs_oracle_batched(eng, golden):
+    """many sims per root, several roots per call, against the C oracle"""
+    from visapi_b200 import pack_occupancy, pack_tiles
+    cases = [c for c in golden("rollouts.json") if c["sim"] == 0 and "board" not in c]
+    by_shape = {}
+    for c in cases:
+        by_shape.setdefault((c["rows"], c["cols"], len(c["tiles"])), []).append(c)
+    n_sims = 70
+    for (rows, cols, E), grp in by_shape.items():
+        occ = pack_occupancy(np.zeros((len(grp), rows, cols)))
+        tiles = pack_tiles([c["tiles"] for c in grp])
+        streams = [c["stream"] for c in grp]
+        tags = [c["tag"] for c in grp]
+        steps, solved, _ = eng.rollouts(occ, cols, tiles, n_sims, seed=99, streams=streams,
+                                        tags=tags, sim_begin=5)
+        for k, c in enumerate(grp):
+            for s in range(0, n_sims, 7):
+                o = c_oracle.rollout(np.zeros((rows, cols)), c["tiles"], 99, c["stream"], c["tag"], 5 + s)
+                assert bool(solved[k, s]) == o["solved"]
+                assert int(steps[k, s]) == o["placements"]
+
+
+FLAT_KEYS = ["depth", "solution_found", "score", "n_tiles_placed", "rollouts", "rollout_placements"]
+
+
+def _check_flat(case, res, i, n_sim, strategy):
+    for k in FLAT_KEYS:
+        assert int(res[k][i]) == int(case[k]), (case["name"], strategy, k, int(res[k][i]), case[k])
+    n_order = int(res["n_order"][i])
+    assert res["order"][i, :n_order].tolist() == case["solution_tiles_order"]
+    # every child's score
+    E = res["child_scores"].shape[2]
+    want = {}
+    for d, e, sc in case["children"]:
+        if sc == "S":
+            want[(d, e)] = -2
+        else:
+            want[(d, e)] = int(round(sc * n_sim)) if strategy == "avg_depth" else int(sc)
+    got = {}
+    for d in range(res["child_scores"].shape[1]):
+        for e in range(E):
+            v = int(res["child_scores"][i, d, e])
+            if v != -1:
+                got[(d, e)] = v
+    assert got == want, (case["name"], strategy)
+
+
+def test_flat_search_golden(eng, golden):
+    from visapi_b200 import pack_tiles
+    cases = golden("flat_search.json")
+    groups = {}
+    for c in cases:
+        groups.setdefault((c["n_sim"], c["strategy"], len(c["tiles"])), []).append(c)
+    for (n_sim, strategy, E), grp in groups.items():
+        res = eng.flat_search([c["rows"] for c in grp], [c["cols"] for c in grp],
+                              pack_tiles([c["tiles"] for c in grp]), [E] * len(grp), n_sim,
+                              strategy=0 if strategy == "max_depth" else 1, seed=123,
+                              streams=[c["stream"] for c in grp], want_scores=True)
+        for i, c in enumerate(grp):
+            _check_flat(c, res, i, n_sim, strategy)
+
+
+def test_flat_search_mixed_entry_counts(eng, golden):
+    """problems with different tile counts in one batch (entry stride padding)"""
+    from visapi_b200 import pack_tiles
+    cases = [c for c in golden("flat_search.json") if c["n_sim"] == 5 and c["strategy"] == "max_depth"]
+    assert len({len(c["tiles"]) for c in cases}) > 1 or len(cases) > 4
+    ES = max(len(c["tiles"]) for c in cases)
+    res = eng.flat_search([c["rows"] for c in cases], [c["cols"] for c in cases],
+                          pack_tiles([c["tiles"] for c in cases], ES),
+                          [len(c["tiles"]) for c in cases], 5, strategy=0, seed=123,
+                          streams=[c["stream"] for c in cases], want_scores=True)
+    for i, c in enumerate(cases):
+        _check_flat(c, res, i, 5, "max_depth")

@@ -1,0 +1,75 @@
+"""Builds visapi_b200/librectpack_b200.so (sm_100a only) with nvcc, in tree.
+
+    python -m visapi_b200.build [--force]
+
+The shared library is git-ignored but travels to the GPU box with the snapshot.
+"""
+import concurrent.futures
+import os
+import shutil
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OBJ_DIR = os.path.join(CSRC, "build")
+LIB_PATH = os.path.join(HERE, "librectpack_b200.so")
+SOURCES = ["api_basic.cu", "flat_search.cu", "puct.cu"]
+HEADERS = ["board.cuh", "philox.cuh", "common.cuh", os.path.join("..", "..", "include", "rectpack_b200.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a",
+    "-std=c++17", "-O3", "-lineinfo",
+    "-Xcompiler", "-fPIC",
+    "--threads", "2",
+]
+
+
+def nvcc():
+    exe = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(exe):
+        raise RuntimeError("nvcc not found; rectpack_b200 cannot be built")
+    return exe
+
+
+def _mtime(path):
+    return os.path.getmtime(path) if os.path.exists(path) else 0.0
+
+
+def _sources():
+    return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
+
+
+def stale():
+    deps = [os.path.join(CSRC, s) for s in _sources()] + [os.path.join(CSRC, h) for h in HEADERS]
+    return _mtime(LIB_PATH) < max(_mtime(d) for d in deps)
+
+
+def _compile(src):
+    obj = os.path.join(OBJ_DIR, src.replace(".cu", ".o"))
+    cmd = [nvcc()] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, proc.stdout, proc.stderr))
+    return obj
+
+
+def build(force=False, verbose=True):
+    if not force and not stale():
+        return LIB_PATH
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    srcs = _sources()
+    if verbose:
+        print("[visapi_b200] nvcc sm_100a: %s" % ", ".join(srcs), file=sys.stderr)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=len(srcs)) as pool:
+        objs = list(pool.map(_compile, srcs))
+    cmd = [nvcc(), "-shared", "-o", LIB_PATH] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                        "-cudart", "static"]
+    proc = subprocess.run(cmd, capture_output=True, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError("link failed:\n%s\n%s" % (proc.stdout, proc.stderr))
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv))

@@ -1,0 +1,810 @@
+// Flat Monte-Carlo search (CustomMCTS.predict, binpack/MCTS.py:44-149) resident on the
+// device: many problems in flight, every depth = one rollout launch + one advance launch
+// per shape class, no host round trip until the results are read.
+//
+// HBM layout (P problems, ES = entry stride, RS/WS = max rows / words per row of the batch):
+//   desc[P]            rows, cols, n_entries, class, Philox stream           (read-only)
+//   occ[P][RS][WS]     current board of each problem (row-major words)
+//   tiles[P][ES][2]    current live tile list, compacted, (0,0) padded
+//   lfb[P]             (row, col, free run, live entries) of the current board
+//   legal[P]           4 x 32-bit legal-entry masks of the current board
+//   rec[P][ES][NC]     one 8-byte record per (child, chunk of 32 rollouts)
+//   stats[P][ES]       per-child statistics (root-parallel exchange buffer)
+//   child_list[]       (problem, entry) of every child of the current depth, per class
+// A rollout never touches HBM except to read its root (once per 32 rollouts) and to
+// write 8 bytes per 32 rollouts; it is bound by instruction issue, not bandwidth.
+#include <algorithm>
+#include <cstring>
+#include <vector>
+
+#include "board.cuh"
+#include "common.cuh"
+
+namespace bp {
+
+constexpr int CHUNK = 32;              // rollouts per task = one result per lane
+constexpr int ADV_WARPS = 4;
+constexpr uint32_t NONE_U32 = 0xFFFFFFFFu;
+constexpr int MAX_DEPTHS = BP_MAX_ENTRIES / 2 + 1;
+
+enum Status : int { ST_ACTIVE = 0, ST_SOLVED = 1, ST_DEAD = 2 };
+
+struct ProblemDesc {
+    int rows, cols, n_entries, cls;
+    uint32_t stream;
+    int pad0, pad1, pad2;
+};
+
+struct __align__(8) ChunkRec {
+    uint8_t max_steps;       // max placements over the chunk's rollouts
+    uint8_t solved_lane;     // first solved rollout of the chunk, 0xFF = none
+    uint16_t sum_steps;      // placements of all rollouts of the chunk
+    uint16_t prefix_steps;   // placements of rollouts 0..solved_lane (== sum when none)
+    uint16_t n_sims;
+};
+
+struct __align__(8) ChildStats {
+    int32_t max_steps;
+    uint32_t first_solved;   // global sim index of the first solved rollout, NONE_U32 = none
+    long long sum_steps;     // placements over all of this rank's rollouts
+    long long prefix_steps;  // placements up to and including first_solved (this rank)
+};
+
+struct SearchParams {
+    int n_problems, es, rs, ws;
+    int n_sim, strategy, n_chunks;          // n_chunks: chunks of THIS rank
+    int sim_begin, n_local, rank, n_ranks;
+    uint32_t seed;
+    const ProblemDesc* desc;
+    uint32_t* occ;
+    uint8_t* tiles;
+    int4* lfb;
+    uint4* legal;
+    int* status;
+    int* depth;
+    unsigned long long* n_tiles_placed;
+    unsigned long long* rollouts;
+    unsigned long long* rollout_placements;
+    unsigned long long* rollouts_executed;
+    uint16_t* prev_tile;
+    int* n_order;
+    uint8_t* order;          // [P][ES/2+2][2]
+    int* path;               // [P][ES/2]
+    int* child_scores;       // [P][ES/2][ES]
+    ChunkRec* rec;           // [P][ES][NC]
+    ChildStats* stats;       // [P][ES]
+    uint32_t* child_list;    // per class segments
+    unsigned* child_count;   // [MAX_DEPTHS + 1][N_CLASSES]
+    unsigned* task_counter;  // [MAX_DEPTHS + 1][N_CLASSES]
+};
+
+__device__ __forceinline__ long long warp_sum_ll(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULLMASK, v, o);
+    return v;
+}
+
+// ------------------------------------------------------------------ rollout kernel
+// Persistent warps pull (child, chunk) tasks; a task builds the child board from its
+// parent (one placement) and plays CHUNK rollouts from it.
+template <int RHO, int W, int EJ>
+__global__ void __launch_bounds__(128)
+fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
+{
+    const int lane = lane_id();
+    const unsigned n_children = p.child_count[depth_slot * N_CLASSES + cls];
+    const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
+    unsigned* counter = &p.task_counter[depth_slot * N_CLASSES + cls];
+    for (;;) {
+        unsigned long long task = 0;
+        if (lane == 0) task = atomicAdd(counter, 1u);
+        task = __shfl_sync(FULLMASK, task, 0);
+        if (task >= n_tasks) break;
+        const unsigned child = (unsigned)(task / p.n_chunks);
+        const int chunk = (int)(task % p.n_chunks);
+        const uint32_t packed = p.child_list[cls_list_offset + child];
+        const int prob = (int)(packed & 0xFFFFFFu);
+        const int entry = (int)(packed >> 24);
+        const ProblemDesc d = p.desc[prob];
+        const int4 lfb = p.lfb[prob];
+
+        WarpState<RHO, W, EJ> s;
+        load_board(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
+        load_entries(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
+        uint32_t mine = s.ent[0];
+#pragma unroll
+        for (int j = 1; j < EJ; ++j) mine = ((entry >> 5) == j) ? s.ent[j] : mine;
+        const uint32_t v = __shfl_sync(FULLMASK, mine, entry & 31);
+        place(s, lfb.x, lfb.y, (int)(v & 0xFFu), (int)(v >> 8));
+        kill_pair(s, v);
+        const int n_alive = lfb.w - 2;
+        const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
+
+        const int first = chunk * CHUNK;
+        const int count = min(CHUNK, p.n_local - first);
+        int my_steps = 0;
+        bool my_solved = false;
+        for (int i = 0; i < count; ++i) {
+            bool solved;
+            const int steps = rollout<RHO, W, EJ, false>(
+                s, d.rows, n_alive, p.seed, d.stream, tag, (uint32_t)(p.sim_begin + first + i),
+                solved, nullptr);
+            if (lane == i) { my_steps = steps; my_solved = solved; }
+        }
+        const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved);
+        const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
+        const int mx = __reduce_max_sync(FULLMASK, my_steps);
+        const int sum = __reduce_add_sync(FULLMASK, my_steps);
+        const int pre = __reduce_add_sync(FULLMASK, (lane <= first_lane) ? my_steps : 0);
+        if (lane == 0) {
+            ChunkRec r;
+            r.max_steps = (uint8_t)mx;
+            r.solved_lane = (uint8_t)first_lane;
+            r.sum_steps = (uint16_t)sum;
+            r.prefix_steps = (uint16_t)pre;
+            r.n_sims = (uint16_t)count;
+            p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
+        }
+    }
+}
+
+// --------------------------------------------------------- per-child statistics
+// this rank's statistics of child `entry` of problem `prob`, from its chunk records
+__device__ __forceinline__ ChildStats stats_from_records(const SearchParams& p, int prob, int entry)
+{
+    const ChunkRec* rec = p.rec + ((size_t)prob * p.es + entry) * p.n_chunks;
+    ChildStats st;
+    st.max_steps = 0;
+    st.first_solved = NONE_U32;
+    st.sum_steps = 0;
+    st.prefix_steps = 0;
+    for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const ChunkRec r = rec[ch];
+        st.max_steps = max(st.max_steps, (int)r.max_steps);
+        st.sum_steps += r.sum_steps;
+        if (st.first_solved == NONE_U32) {
+            if (r.solved_lane != 0xFF) {
+                st.first_solved = (uint32_t)(p.sim_begin + ch * CHUNK + r.solved_lane);
+                st.prefix_steps += r.prefix_steps;
+            } else {
+                st.prefix_steps += r.sum_steps;
+            }
+        }
+    }
+    return st;
+}
+
+// merge the per-rank statistics (ranks hold ascending contiguous sim ranges)
+__device__ __forceinline__ ChildStats stats_from_gathered(const SearchParams& p,
+                                                          const ChildStats* gathered, int prob,
+                                                          int entry)
+{
+    ChildStats st;
+    st.max_steps = 0;
+    st.first_solved = NONE_U32;
+    st.sum_steps = 0;
+    st.prefix_steps = 0;
+    for (int g = 0; g < p.n_ranks; ++g) {
+        const ChildStats r = gathered[((size_t)g * p.n_problems + prob) * p.es + entry];
+        st.max_steps = max(st.max_steps, r.max_steps);
+        st.sum_steps += r.sum_steps;
+        if (st.first_solved == NONE_U32) {
+            st.prefix_steps += r.prefix_steps;     // == r.sum_steps when r has no solved sim
+            st.first_solved = r.first_solved;
+        }
+    }
+    return st;
+}
+
+template <int EJ>
+__global__ void __launch_bounds__(ADV_WARPS * 32)
+fs_reduce_kernel(SearchParams p, const int* __restrict__ cls_problems, int n_cls_problems)
+{
+    const int idx = blockIdx.x * ADV_WARPS + (threadIdx.x >> 5);
+    if (idx >= n_cls_problems) return;
+    const int prob = cls_problems[idx];
+    if (p.status[prob] != ST_ACTIVE) return;
+    const int lane = lane_id();
+    const uint4 lg = p.legal[prob];
+    const uint32_t legal[4] = {lg.x, lg.y, lg.z, lg.w};
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) {
+        if ((legal[j] >> lane) & 1u) {
+            const int e = lane + 32 * j;
+            p.stats[(size_t)prob * p.es + e] = stats_from_records(p, prob, e);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ advance kernel
+// One warp per problem.  FIRST: set up depth 0.  Otherwise: score the children of the
+// current depth (lane = child), stop at the first child with a solved rollout, else commit
+// the first maximum; then expand the new state (LFB, legal entries, child list).
+template <int RHO, int W, int EJ>
+__device__ __forceinline__ void compact_entries_adv(WarpState<RHO, W, EJ>& s, uint16_t* buf)
+{
+    const int lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) buf[lane + 32 * j] = 0;
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) {
+        const uint32_t m = __ballot_sync(FULLMASK, s.ent[j] != 0u);
+        if (s.ent[j] != 0u) buf[base + __popc(m & lt)] = (uint16_t)s.ent[j];
+        base += __popc(m);
+    }
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) s.ent[j] = buf[lane + 32 * j];
+    __syncwarp();
+}
+
+template <int RHO, int W, int EJ, bool FIRST>
+__global__ void __launch_bounds__(ADV_WARPS * 32)
+fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
+                  const int* __restrict__ cls_problems, int n_cls_problems, int next_slot,
+                  const ChildStats* __restrict__ gathered)
+{
+    __shared__ uint16_t cbuf[ADV_WARPS][32 * EJ];
+    const int warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * ADV_WARPS + warp;
+    if (idx >= n_cls_problems) return;
+    const int prob = cls_problems[idx];
+    const int lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    const ProblemDesc d = p.desc[prob];
+
+    WarpState<RHO, W, EJ> s;
+    int n_alive;
+    if (FIRST) {
+        load_board(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
+        load_entries(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
+        compact_entries_adv(s, cbuf[warp]);
+        n_alive = count_alive(s);
+    } else {
+        if (p.status[prob] != ST_ACTIVE) return;
+        const int depth = p.depth[prob];
+        const int4 lfb = p.lfb[prob];
+        n_alive = lfb.w;
+        const uint4 lg = p.legal[prob];
+        const uint32_t legal[4] = {lg.x, lg.y, lg.z, lg.w};
+        load_board(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
+        load_entries(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
+
+        // ---- per-child statistics, lane = child ---------------------------------
+        ChildStats st[EJ];
+        uint32_t solved_m[EJ];
+        int first_child = -1;
+#pragma unroll
+        for (int j = 0; j < EJ; ++j) {
+            const int e = lane + 32 * j;
+            const bool is_child = (legal[j] >> lane) & 1u;
+            st[j].max_steps = 0; st[j].first_solved = NONE_U32;
+            st[j].sum_steps = 0; st[j].prefix_steps = 0;
+            if (is_child)
+                st[j] = gathered ? stats_from_gathered(p, gathered, prob, e)
+                                 : stats_from_records(p, prob, e);
+            solved_m[j] = __ballot_sync(FULLMASK, is_child && st[j].first_solved != NONE_U32);
+            if (first_child < 0 && solved_m[j]) first_child = 32 * j + __ffs(solved_m[j]) - 1;
+        }
+
+        // ---- what the reference would have counted (MCTS.py:60,76,134-140) -------
+        long long roll = 0, plc = 0;
+        int best_score = -1, best_entry = -1;
+        int* scores = p.child_scores + ((size_t)prob * (p.es / 2) + depth) * p.es;
+#pragma unroll
+        for (int j = 0; j < EJ; ++j) {
+            const int e = lane + 32 * j;
+            const bool is_child = (legal[j] >> lane) & 1u;
+            int score = -1;
+            if (is_child) {
+                if (first_child < 0 || e < first_child) {
+                    roll += p.n_sim;
+                    plc += st[j].sum_steps;
+                    score = p.strategy == BP_MAX_DEPTH ? st[j].max_steps : (int)st[j].sum_steps;
+                } else if (e == first_child) {
+                    roll += (long long)st[j].first_solved + 1;
+                    plc += st[j].prefix_steps;
+                    score = -2;
+                }
+            }
+            if (e < p.es) scores[e] = score;
+            // first maximum in entry order (get_max_index, MCTS.py:20-29)
+            const int key_score = (is_child && score >= 0) ? score : -1;
+            const int mx = __reduce_max_sync(FULLMASK, key_score);
+            if (mx > best_score) {                               // strict: earlier j wins ties
+                const uint32_t who = __ballot_sync(FULLMASK, key_score == mx);
+                best_score = mx;
+                best_entry = 32 * j + __ffs(who) - 1;
+            }
+        }
+        roll = warp_sum_ll(roll);
+        plc = warp_sum_ll(plc);
+        if (lane == 0) {
+            p.rollouts[prob] += (unsigned long long)roll;
+            p.rollout_placements[prob] += (unsigned long long)plc;
+            p.n_tiles_placed[prob] += (unsigned long long)plc;
+        }
+
+        const int take = first_child >= 0 ? first_child : best_entry;
+        uint32_t mine = s.ent[0];
+#pragma unroll
+        for (int j = 1; j < EJ; ++j) mine = ((take >> 5) == j) ? s.ent[j] : mine;
+        const uint32_t v = __shfl_sync(FULLMASK, mine, take & 31);
+        const uint16_t prev = p.prev_tile[prob];
+        int n_order = p.n_order[prob];
+        uint8_t* order = p.order + (size_t)prob * (p.es / 2 + 2) * 2;
+
+        place(s, lfb.x, lfb.y, (int)(v & 0xFFu), (int)(v >> 8));
+        kill_pair(s, v);
+
+        if (first_child >= 0) {
+            // ---- solved inside a rollout (MCTS.py:77-93) -------------------------
+            if (lane == 0) {
+                // entries after the solving child were never attempted (:58-60)
+                p.n_tiles_placed[prob] -= (unsigned long long)(n_alive - first_child - 1);
+                if (prev) { order[2 * n_order] = prev & 0xFF; order[2 * n_order + 1] = prev >> 8; n_order++; }
+                order[2 * n_order] = v & 0xFF; order[2 * n_order + 1] = v >> 8; n_order++;
+            }
+            n_order = __shfl_sync(FULLMASK, n_order, 0);
+            // replay the winning rollout to recover its move list
+            uint32_t sim = NONE_U32;
+#pragma unroll
+            for (int j = 0; j < EJ; ++j) {
+                const uint32_t cand = __shfl_sync(FULLMASK, st[j].first_solved, first_child & 31);
+                sim = ((first_child >> 5) == j) ? cand : sim;
+            }
+            bool solved;
+            const uint32_t tag = ((uint32_t)depth << 16) | (uint32_t)first_child;
+            const int steps = rollout<RHO, W, EJ, true>(s, d.rows, n_alive - 2, p.seed, d.stream, tag,
+                                                        sim, solved, order + 2 * n_order);
+            if (lane == 0) {
+                p.n_order[prob] = n_order + steps;
+                p.status[prob] = solved ? ST_SOLVED : ST_DEAD;   // solved is always true here
+            }
+            return;
+        }
+
+        // ---- commit the best child (MCTS.py:105-119) -----------------------------
+        compact_entries_adv(s, cbuf[warp]);
+        n_alive -= 2;
+        if (lane == 0) {
+            if (prev) { order[2 * n_order] = prev & 0xFF; order[2 * n_order + 1] = prev >> 8; n_order++; }
+            p.n_order[prob] = n_order;
+            p.prev_tile[prob] = (uint16_t)v;
+            p.path[(size_t)prob * (p.es / 2) + depth] = best_entry;
+            p.depth[prob] = depth + 1;
+        }
+        store_board(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
+    }
+    store_entries(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
+
+    // ---- expand: LFB, legal entries, children of the next depth ----------------
+    int status = ST_ACTIVE;
+    int r = -1, c = -1, run = 0, k = 0;
+    uint32_t legal[EJ];
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) legal[j] = 0u;
+    if (n_alive == 0) {
+        status = ST_SOLVED;                                  // MCTS.py:121-123
+    } else if (!find_lfb(s, r, c, run)) {
+        status = ST_DEAD;                                    // full board, tiles left
+    } else {
+        k = legal_masks(s, d.rows, r, run, legal);
+        if (k == 0) status = ST_DEAD;                        // MCTS.py:101-103
+    }
+    unsigned base = 0;
+    if (lane == 0) {
+        p.status[prob] = status;
+        p.lfb[prob] = make_int4(r, c, run, n_alive);
+        uint4 lg = make_uint4(legal[0], EJ > 1 ? legal[EJ > 1 ? 1 : 0] : 0u,
+                              EJ > 2 ? legal[EJ > 2 ? 2 : 0] : 0u, EJ > 3 ? legal[EJ > 3 ? 3 : 0] : 0u);
+        p.legal[prob] = lg;
+        if (status != ST_SOLVED && n_alive > 0 && r >= 0)
+            p.n_tiles_placed[prob] += (unsigned long long)n_alive;   // one attempt per entry (:60)
+        if (k > 0) {
+            base = atomicAdd(&p.child_count[next_slot * N_CLASSES + cls], (unsigned)k);
+            p.rollouts_executed[prob] += (unsigned long long)k * p.n_local;
+        }
+    }
+    if (k > 0) {
+        base = __shfl_sync(FULLMASK, base, 0);
+#pragma unroll
+        for (int j = 0; j < EJ; ++j) {
+            if ((legal[j] >> lane) & 1u)
+                p.child_list[cls_list_offset + base + __popc(legal[j] & lt)] =
+                    (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
+            base += __popc(legal[j]);
+        }
+    }
+}
+
+}  // namespace bp
+
+// ================================================================= host side
+using namespace bp;
+
+struct bp_search {
+    bp_context* ctx = nullptr;
+    SearchParams p{};
+    int max_depth = 0;
+    int cur_depth = 0;         // next depth to play
+    bool ready = false;
+    // host copies of the static inputs (for reset)
+    std::vector<ProblemDesc> h_desc;
+    std::vector<uint8_t> h_tiles;
+    std::vector<uint32_t> h_boards;
+    // class bookkeeping
+    std::vector<int> classes;                   // classes present
+    int cls_count[N_CLASSES] = {0};
+    int cls_prob_off[N_CLASSES] = {0};          // offset into d_cls_problems
+    int cls_list_off[N_CLASSES] = {0};          // offset into child_list
+    int grid_rollout[N_CLASSES] = {0};
+    int* d_cls_problems = nullptr;
+    ProblemDesc* d_desc = nullptr;
+    std::vector<void*> allocs;
+    size_t counters_bytes = 0;
+};
+
+template <typename T>
+static int dev_alloc(bp_search* s, T** out, size_t count)
+{
+    void* ptr = nullptr;
+    BP_CUDA(cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T)));
+    s->allocs.push_back(ptr);
+    *out = static_cast<T*>(ptr);
+    return BP_OK;
+}
+
+static int alloc_records(bp_search* s)
+{
+    // (re)allocate the chunk records for the current partition
+    SearchParams& p = s->p;
+    if (p.rec) {
+        auto it = std::find(s->allocs.begin(), s->allocs.end(), (void*)p.rec);
+        if (it != s->allocs.end()) s->allocs.erase(it);
+        BP_CUDA(cudaFree(p.rec));
+        p.rec = nullptr;
+    }
+    return dev_alloc(s, &p.rec, (size_t)p.n_problems * p.es * p.n_chunks);
+}
+
+extern "C" {
+
+int bp_search_destroy(bp_search* s)
+{
+    if (!s) return BP_OK;
+    cudaSetDevice(s->ctx->device);
+    cudaStreamSynchronize(s->ctx->stream);
+    for (void* ptr : s->allocs) cudaFree(ptr);
+    delete s;
+    return BP_OK;
+}
+
+int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const int32_t* cols,
+                     const int32_t* n_entries, const uint8_t* tiles, int entry_stride,
+                     const uint32_t* boards, const uint32_t* streams, int n_sim, int strategy,
+                     uint32_t seed, bp_search** out)
+{
+    BP_REQUIRE(ctx && out && rows && cols && n_entries && tiles, "null argument");
+    BP_REQUIRE(n_problems >= 1 && n_problems < (1 << 24), "n_problems must be 1..2^24-1");
+    BP_REQUIRE(entry_stride >= 2 && entry_stride <= BP_MAX_ENTRIES && entry_stride % 2 == 0,
+               "entry_stride must be even, 2..128");
+    BP_REQUIRE(n_sim >= 1 && n_sim <= (1 << 24), "n_sim must be 1..2^24");
+    BP_REQUIRE(strategy == BP_MAX_DEPTH || strategy == BP_AVG_DEPTH, "strategy");
+    int rs = 0, max_cols = 0, max_n = 0;
+    for (int i = 0; i < n_problems; ++i) {
+        BP_REQUIRE(shape_ok(rows[i], cols[i], n_entries[i]) && n_entries[i] <= entry_stride &&
+                       n_entries[i] % 2 == 0,
+                   "problem shape out of range (rows, cols 1..128; entries even, <= entry_stride)");
+        rs = std::max(rs, rows[i]);
+        max_cols = std::max(max_cols, cols[i]);
+        max_n = std::max(max_n, n_entries[i] / 2);
+    }
+    BP_CUDA(cudaSetDevice(ctx->device));
+    bp_search* s = new bp_search();
+    s->ctx = ctx;
+    SearchParams& p = s->p;
+    p.n_problems = n_problems;
+    p.es = entry_stride;
+    p.rs = rs;
+    p.ws = (max_cols + 31) / 32;
+    p.n_sim = n_sim;
+    p.strategy = strategy;
+    p.seed = seed;
+    p.sim_begin = 0;
+    p.n_local = n_sim;
+    p.rank = 0;
+    p.n_ranks = 1;
+    p.n_chunks = (n_sim + CHUNK - 1) / CHUNK;
+    s->max_depth = max_n;
+
+    s->h_desc.resize(n_problems);
+    std::vector<std::vector<int>> by_class(N_CLASSES);
+    for (int i = 0; i < n_problems; ++i) {
+        ProblemDesc& d = s->h_desc[i];
+        d.rows = rows[i]; d.cols = cols[i]; d.n_entries = n_entries[i];
+        d.cls = shape_class(rows[i], cols[i], n_entries[i]);
+        d.stream = streams ? streams[i] : (uint32_t)i;
+        d.pad0 = d.pad1 = d.pad2 = 0;
+        by_class[d.cls].push_back(i);
+    }
+    s->h_tiles.assign(tiles, tiles + (size_t)n_problems * entry_stride * 2);
+    if (boards) s->h_boards.assign(boards, boards + (size_t)n_problems * p.rs * p.ws);
+
+    std::vector<int> cls_problems;
+    int list_off = 0;
+    for (int c = 0; c < N_CLASSES; ++c) {
+        s->cls_count[c] = (int)by_class[c].size();
+        s->cls_prob_off[c] = (int)cls_problems.size();
+        s->cls_list_off[c] = list_off;
+        if (s->cls_count[c]) {
+            s->classes.push_back(c);
+            cls_problems.insert(cls_problems.end(), by_class[c].begin(), by_class[c].end());
+            list_off += s->cls_count[c] * entry_stride;
+        }
+    }
+
+    int rc = BP_OK;
+#define TRY(x) do { rc = (x); if (rc) { bp_search_destroy(s); return rc; } } while (0)
+    const size_t P = n_problems;
+    TRY(dev_alloc(s, &s->d_desc, P));
+    p.desc = s->d_desc;
+    TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));
+    TRY(dev_alloc(s, &p.tiles, P * p.es * 2));
+    TRY(dev_alloc(s, &p.lfb, P));
+    TRY(dev_alloc(s, &p.legal, P));
+    TRY(dev_alloc(s, &p.status, P));
+    TRY(dev_alloc(s, &p.depth, P));
+    TRY(dev_alloc(s, &p.n_tiles_placed, P));
+    TRY(dev_alloc(s, &p.rollouts, P));
+    TRY(dev_alloc(s, &p.rollout_placements, P));
+    TRY(dev_alloc(s, &p.rollouts_executed, P));
+    TRY(dev_alloc(s, &p.prev_tile, P));
+    TRY(dev_alloc(s, &p.n_order, P));
+    TRY(dev_alloc(s, &p.order, P * (p.es / 2 + 2) * 2));
+    TRY(dev_alloc(s, &p.path, P * (p.es / 2)));
+    TRY(dev_alloc(s, &p.child_scores, P * (p.es / 2) * p.es));
+    TRY(dev_alloc(s, &p.stats, P * p.es));
+    TRY(dev_alloc(s, &p.child_list, (size_t)std::max(list_off, 1)));
+    s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * N_CLASSES * sizeof(unsigned);
+    TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * N_CLASSES));
+    TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * N_CLASSES));
+    TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
+    TRY(alloc_records(s));
+#undef TRY
+    BP_CUDA(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    BP_CUDA(cudaMemcpyAsync(s->d_cls_problems, cls_problems.data(), cls_problems.size() * sizeof(int),
+                            cudaMemcpyHostToDevice, ctx->stream));
+    BP_CUDA(cudaStreamSynchronize(ctx->stream));
+
+    // persistent grid per class: every SM filled to the occupancy limit of that kernel
+    for (int c : s->classes) {
+        int per_sm = 1;
+        dispatch_class(c, [&](auto R, auto Wc, auto E) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &per_sm, fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>,
+                128, 0);
+        });
+        s->grid_rollout[c] = ctx->sm_count * std::max(per_sm, 1);
+    }
+    *out = s;
+    return BP_OK;
+}
+
+int bp_search_set_partition(bp_search* s, int rank, int n_ranks, int sim_begin, int n_local)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    BP_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    BP_REQUIRE(sim_begin >= 0 && n_local >= 0 && sim_begin + n_local <= s->p.n_sim, "sim range");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    BP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    s->p.rank = rank;
+    s->p.n_ranks = n_ranks;
+    s->p.sim_begin = sim_begin;
+    s->p.n_local = n_local;
+    s->p.n_chunks = std::max(1, (n_local + CHUNK - 1) / CHUNK);
+    s->ready = false;
+    return alloc_records(s);
+}
+
+}  // extern "C"
+
+template <bool FIRST>
+static void launch_advance(bp_search* s, int next_slot, const ChildStats* gathered)
+{
+    for (int c : s->classes) {
+        const int n = s->cls_count[c];
+        const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
+        dispatch_class(c, [&](auto R, auto Wc, auto E) {
+            fs_advance_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value, FIRST>
+                <<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(
+                    s->p, c, s->cls_list_off[c], s->d_cls_problems + s->cls_prob_off[c], n,
+                    next_slot, gathered);
+        });
+        s->ctx->launches++;
+    }
+}
+
+extern "C" {
+
+int bp_search_reset(bp_search* s)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    bp_context* ctx = s->ctx;
+    SearchParams& p = s->p;
+    BP_CUDA(cudaSetDevice(ctx->device));
+    const size_t P = p.n_problems;
+    cudaStream_t st = ctx->stream;
+    if (s->h_boards.empty())
+        BP_CUDA(cudaMemsetAsync(p.occ, 0, P * p.rs * p.ws * 4, st));
+    else
+        BP_CUDA(cudaMemcpyAsync(p.occ, s->h_boards.data(), P * p.rs * p.ws * 4, cudaMemcpyHostToDevice, st));
+    BP_CUDA(cudaMemcpyAsync(p.tiles, s->h_tiles.data(), P * p.es * 2, cudaMemcpyHostToDevice, st));
+    BP_CUDA(cudaMemsetAsync(p.status, 0, P * sizeof(int), st));
+    BP_CUDA(cudaMemsetAsync(p.depth, 0, P * sizeof(int), st));
+    BP_CUDA(cudaMemsetAsync(p.n_tiles_placed, 0, P * 8, st));
+    BP_CUDA(cudaMemsetAsync(p.rollouts, 0, P * 8, st));
+    BP_CUDA(cudaMemsetAsync(p.rollout_placements, 0, P * 8, st));
+    BP_CUDA(cudaMemsetAsync(p.rollouts_executed, 0, P * 8, st));
+    BP_CUDA(cudaMemsetAsync(p.prev_tile, 0, P * 2, st));
+    BP_CUDA(cudaMemsetAsync(p.n_order, 0, P * sizeof(int), st));
+    BP_CUDA(cudaMemsetAsync(p.order, 0, P * (p.es / 2 + 2) * 2, st));
+    BP_CUDA(cudaMemsetAsync(p.path, 0xFF, P * (p.es / 2) * sizeof(int), st));
+    BP_CUDA(cudaMemsetAsync(p.child_scores, 0xFF, P * (p.es / 2) * p.es * sizeof(int), st));
+    BP_CUDA(cudaMemsetAsync(p.child_count, 0, s->counters_bytes, st));
+    BP_CUDA(cudaMemsetAsync(p.task_counter, 0, s->counters_bytes, st));
+    launch_advance<true>(s, 0, nullptr);
+    BP_CUDA(cudaGetLastError());
+    s->cur_depth = 0;
+    s->ready = true;
+    return BP_OK;
+}
+
+int bp_search_step_rollouts(bp_search* s)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    if (!s->ready || s->cur_depth >= s->max_depth) {
+        set_error("bp_search_step_rollouts: call bp_search_reset first / search finished");
+        return BP_ERR_STATE;
+    }
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    for (int c : s->classes) {
+        dispatch_class(c, [&](auto R, auto Wc, auto E) {
+            fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
+                <<<s->grid_rollout[c], 128, 0, s->ctx->stream>>>(s->p, c, s->cls_list_off[c],
+                                                                 s->cur_depth);
+        });
+        s->ctx->launches++;
+    }
+    BP_CUDA(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_search_step_reduce(bp_search* s)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    for (int c : s->classes) {
+        const int n = s->cls_count[c];
+        const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
+        const int ej = c % 3 == 0 ? 1 : (c % 3 == 1 ? 2 : 4);
+        const int* list = s->d_cls_problems + s->cls_prob_off[c];
+        if (ej == 1) fs_reduce_kernel<1><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
+        else if (ej == 2) fs_reduce_kernel<2><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
+        else fs_reduce_kernel<4><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
+        s->ctx->launches++;
+    }
+    BP_CUDA(cudaGetLastError());
+    return BP_OK;
+}
+
+int bp_search_step_commit(bp_search* s, const void* gathered_stats_dev)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    if (!s->ready || s->cur_depth >= s->max_depth) {
+        set_error("bp_search_step_commit: no depth in flight");
+        return BP_ERR_STATE;
+    }
+    BP_REQUIRE(s->p.n_ranks == 1 || gathered_stats_dev != nullptr,
+               "a partitioned search needs the gathered statistics of all ranks");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    launch_advance<false>(s, s->cur_depth + 1, static_cast<const ChildStats*>(gathered_stats_dev));
+    BP_CUDA(cudaGetLastError());
+    s->cur_depth += 1;
+    return BP_OK;
+}
+
+int bp_search_stats_buffer(bp_search* s, void** stats_dev, int64_t* n_bytes)
+{
+    BP_REQUIRE(s && stats_dev && n_bytes, "null argument");
+    *stats_dev = s->p.stats;
+    *n_bytes = (int64_t)s->p.n_problems * s->p.es * (int64_t)sizeof(ChildStats);
+    return BP_OK;
+}
+
+int bp_search_max_depth(bp_search* s, int* max_depth)
+{
+    BP_REQUIRE(s && max_depth, "null argument");
+    *max_depth = s->max_depth;
+    return BP_OK;
+}
+
+int bp_search_run(bp_search* s)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    if (s->p.n_ranks != 1) {
+        set_error("bp_search_run is single-rank; use the step API with a partition");
+        return BP_ERR_STATE;
+    }
+    while (s->cur_depth < s->max_depth) {
+        int rc = bp_search_step_rollouts(s);
+        if (rc) return rc;
+        rc = bp_search_step_commit(s, nullptr);
+        if (rc) return rc;
+    }
+    return BP_OK;
+}
+
+int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, int32_t* path,
+                      int32_t* child_scores)
+{
+    BP_REQUIRE(s && results, "null argument");
+    bp_context* ctx = s->ctx;
+    const SearchParams& p = s->p;
+    BP_CUDA(cudaSetDevice(ctx->device));
+    const size_t P = p.n_problems;
+    std::vector<int> status(P), depth(P), n_order(P);
+    std::vector<unsigned long long> ntp(P), roll(P), plc(P), exe(P);
+    cudaStream_t st = ctx->stream;
+    BP_CUDA(cudaMemcpyAsync(status.data(), p.status, P * 4, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(depth.data(), p.depth, P * 4, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(n_order.data(), p.n_order, P * 4, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(ntp.data(), p.n_tiles_placed, P * 8, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(roll.data(), p.rollouts, P * 8, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(plc.data(), p.rollout_placements, P * 8, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(exe.data(), p.rollouts_executed, P * 8, cudaMemcpyDeviceToHost, st));
+    if (order)
+        BP_CUDA(cudaMemcpyAsync(order, p.order, P * (p.es / 2 + 2) * 2, cudaMemcpyDeviceToHost, st));
+    if (path)
+        BP_CUDA(cudaMemcpyAsync(path, p.path, P * (p.es / 2) * 4, cudaMemcpyDeviceToHost, st));
+    if (child_scores)
+        BP_CUDA(cudaMemcpyAsync(child_scores, p.child_scores, P * (p.es / 2) * p.es * 4,
+                                cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaStreamSynchronize(st));
+    for (size_t i = 0; i < P; ++i) {
+        bp_search_result& r = results[i];
+        r.depth = depth[i];
+        r.solution_found = status[i] == ST_SOLVED ? 1 : 0;
+        r.score = r.solution_found ? 0 : s->h_desc[i].n_entries / 2 - depth[i];
+        r.n_order = n_order[i];
+        r.n_tiles_placed = (int64_t)ntp[i];
+        r.rollouts = (int64_t)roll[i];
+        r.rollout_placements = (int64_t)plc[i];
+        r.rollouts_executed = (int64_t)exe[i];
+    }
+    return BP_OK;
+}
+
+int bp_flat_search(bp_context* ctx, int n_problems, const int32_t* rows, const int32_t* cols,
+                   const int32_t* n_entries, const uint8_t* tiles, int entry_stride,
+                   const uint32_t* boards, const uint32_t* streams, int n_sim, int strategy,
+                   uint32_t seed, bp_search_result* results, uint8_t* order, int32_t* path,
+                   int32_t* child_scores)
+{
+    bp_search* s = nullptr;
+    int rc = bp_search_create(ctx, n_problems, rows, cols, n_entries, tiles, entry_stride, boards,
+                              streams, n_sim, strategy, seed, &s);
+    if (rc) return rc;
+    rc = bp_search_reset(s);
+    if (!rc) rc = bp_search_run(s);
+    if (!rc) rc = bp_search_results(s, results, order, path, child_scores);
+    bp_search_destroy(s);
+    return rc;
+}
+
+}  // extern "C"
