@@ -1,0 +1,425 @@
+#!/usr/bin/env python
+"""Benchmark of the flat Monte-Carlo search hot path (BASELINE.json: MCTS rollouts/s).
+
+    python bench.py --gpus 1 --steps 5 --warmup 3
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+    python bench.py --impl reference --gpus 1 --steps 2 --warmup 1
+
+Workload (config.workload): problems_g — the 1000 Guillotinable 20-tile instances of the
+reference's problems/problems_g.csv, N = 1000 rollouts per child, max_depth strategy,
+Philox key (123, problem index).  A step = one whole flat search of
+every problem of the rank's shard (all depths).  With N GPUs each rank runs the full
+1000-problem set on its own Philox streams (weak scaling, no collective); the
+strong-scaling wall time of the single 1000-problem set is reported under "strong".
+
+value   = rollouts the reference would have made for the same job (its early exits
+          honoured) / device time, initial states resident in HBM.
+e2e     = same metric through the one-shot C-ABI call bp_flat_search with host numpy
+          buffers (allocation, H2D, all depths, D2H inside the timed region).
+roofline: the rollout kernel is bound by instruction issue, not by HBM or tensor
+          cores: achieved = placements executed x A(class) / rollout-kernel
+          time, peak = SMs x 4 schedulers x max SM clock.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+# warp instructions per placement of the rollout kernel, per shape class (RHO, W, EJ);
+# frozen from ncu smsp__inst_executed.sum / placements (profiles/)
+INST_PER_PLACEMENT = {}
+INST_PER_PLACEMENT_DEFAULT = 150.0
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--set", default="g", choices=["g", "b"])
+    ap.add_argument("--n-sim", type=int, default=1000)
+    ap.add_argument("--strategy", default="max_depth", choices=["max_depth", "avg_depth"])
+    ap.add_argument("--n-problems", type=int, default=1000)
+    ap.add_argument("--seed", type=int, default=123)
+    ap.add_argument("--cpu-budget", type=float, default=15.0,
+                    help="seconds of the python-port CPU sample (0 = skip cpu_baseline)")
+    ap.add_argument("--ref-budget", type=float, default=20.0,
+                    help="--impl reference: seconds per step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong", action="store_true")
+    ap.add_argument("--no-verify", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(a):
+    return {"workload": "problems_%s[0:%d] 20-tile instances, flat MC search, N=%d rollouts/child, %s"
+                        % (a.set, a.n_problems, a.n_sim, a.strategy),
+            "set": a.set, "n_problems": a.n_problems, "n_sim": a.n_sim, "strategy": a.strategy,
+            "seed": a.seed, "l2": "none needed: a step streams no input; state lives in registers"}
+
+
+# ------------------------------------------------------------------ reference arm
+def run_cpu_baseline(a, budget, c_problems, skip_python=False):
+    cmd = [sys.executable, "-m", "oracle.cpu_baseline", "--set", a.set, "--n-sim", str(a.n_sim),
+           "--strategy", a.strategy, "--seed", str(a.seed), "--budget", str(budget),
+           "--c-problems", str(c_problems)]
+    if skip_python:
+        cmd.append("--skip-python")
+    out = subprocess.run(cmd, cwd=ROOT, capture_output=True, text=True, timeout=900)
+    if out.returncode != 0:
+        raise RuntimeError("cpu baseline failed: %s" % out.stderr[-2000:])
+    return json.loads(out.stdout.strip().splitlines()[-1])
+
+
+def reference_arm(a):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    samples = []
+    base = None
+    for i in range(a.warmup + a.steps):
+        base = run_cpu_baseline(a, a.ref_budget if i >= a.warmup else min(a.ref_budget, 3.0),
+                                c_problems=8 if i == a.warmup + a.steps - 1 else 0)
+        if i >= a.warmup:
+            samples.append(base["python_port"])
+    rollouts = sum(s["rollouts"] for s in samples)
+    seconds = sum(s["seconds"] for s in samples)
+    value = rollouts / seconds
+    cores = samples[-1]["cores"]
+    sample = ("python/numpy restatement of reference CustomMCTS.predict, %d single-threaded "
+              "processes, problems in order, %.0f s wall budget per step" % (cores, a.ref_budget))
+    line = {
+        "impl": "reference", "metric": "mcts_rollouts_per_s", "value": value, "unit": "rollouts/s",
+        "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
+        "ms_per_step": 1e3 * seconds / max(len(samples), 1), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "reference problem set",
+        "config": workload_config(a),
+        "cpu_baseline": {"value": value, "unit": "rollouts/s", "cores": cores, "kind": "port",
+                         "sample": sample, "cpu_model": base["cpu_model"],
+                         "placements_per_s": sum(s["placements"] for s in samples) / seconds,
+                         "c_port_value": base.get("c_port", {}).get("rollouts_per_s"),
+                         "c_port_sample": "scalar C restatement, %d pthreads, first 8 problems"
+                                          % cores},
+        "e2e": {"value": value, "unit": "rollouts/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler(object):
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.tmp = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=self.tmp, stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        self.tmp.flush()
+        self.tmp.seek(0)
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.tmp.read().splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, v in zip(names, f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.tmp.close()
+        os.unlink(self.tmp.name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
+                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------ our arm
+def shape_class_key(rows, cols, n_entries):
+    def rc(v):
+        return 1 if v <= 1 else (2 if v <= 2 else 4)
+    return "%d,%d,%d" % (rc((rows + 31) // 32), rc((cols + 31) // 32), rc((n_entries + 31) // 32))
+
+
+def our_arm(a):
+    import torch
+    import torch.distributed as dist
+
+    from visapi_b200 import Engine, datasets
+    from visapi_b200.verify import replay_solution
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = torch.device("cuda", local_rank)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    problems = datasets.load_problem_set(a.set)[:a.n_problems]
+    batch = datasets.batch_arrays(problems)
+    P = len(problems)
+    strat = 0 if a.strategy == "max_depth" else 1
+    # weak scaling: every rank searches the whole set on its own Philox streams
+    streams = (np.arange(P, dtype=np.uint32) + np.uint32(rank * P))
+
+    stream = torch.cuda.current_stream()
+    eng = Engine(local_rank, stream=stream.cuda_stream)
+    search = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], a.n_sim,
+                        strat, a.seed, streams)
+
+    def step():
+        search.reset()
+        search.run()
+
+    for _ in range(max(a.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    launches0 = eng.kernel_launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    t_wall0 = time.time()
+    ev0.record(stream)
+    for _ in range(a.steps):
+        step()
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    barrier()
+    wall = time.time() - t_wall0
+    launches = eng.kernel_launches - launches0
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop()
+    res = search.results()
+
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    counts = torch.tensor([float(res["rollouts"].sum()), float(res["rollout_placements"].sum()),
+                           float(res["rollouts_executed"].sum()),
+                           float(res["placements_executed"].sum()),
+                           float(res["solution_found"].sum())], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM)
+    ms_max = float(t.item())
+    rollouts, placements, rollouts_exec, placements_exec, solved = [float(x) for x in counts.tolist()]
+    sec_per_step = ms_max / 1e3 / a.steps
+    value = rollouts / sec_per_step
+
+    # ---- correctness gate: every reported solution is replayed on the host ----------
+    verified = None
+    if not a.no_verify:
+        bad = []
+        for i, p in enumerate(problems):
+            if res["solution_found"][i]:
+                order = res["order"][i, :res["n_order"][i]].tolist()
+                ok, why = replay_solution(p.rows, p.cols, p.tiles, order)
+                if not ok:
+                    bad.append((i, why))
+        if bad:
+            raise SystemExit("INVALID SOLUTIONS reported by the device: %r" % bad[:5])
+        verified = int(res["solution_found"].sum())
+
+    # ---- per-kernel time (CUDA events on the launching stream) ---------------------
+    search.set_profiling(True)
+    step()
+    rollout_ms, advance_ms, n_depths = search.profile()
+    res_p = search.results()
+    search.set_profiling(False)
+    keys = [shape_class_key(p.rows, p.cols, 2 * len(p.tiles)) for p in problems]
+    algo_inst = 0.0
+    by_class = {}
+    for k, pe in zip(keys, res_p["placements_executed"].tolist()):
+        by_class[k] = by_class.get(k, 0) + pe
+    for k, pe in by_class.items():
+        algo_inst += pe * INST_PER_PLACEMENT.get(k, INST_PER_PLACEMENT_DEFAULT)
+    info = eng.device_info()
+    peaks = {}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            peaks = json.load(f)
+    except (OSError, ValueError):
+        pass
+    sm_max_mhz = float(peaks.get("sm_max_mhz") or clocks.get("sm_max_mhz") or 1965.0)
+    issue_peak = info["sm_count"] * 4 * sm_max_mhz * 1e6
+    achieved = algo_inst / (rollout_ms / 1e3)
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    # HBM bytes of the rollout kernel: root state read per task + 8 B record per task
+    n_tasks = float(res_p["rollouts_executed"].sum()) / 32.0
+    algo_bytes = n_tasks * (26 * 2 * 4 + 40 * 2 + 48 + 8)
+    roofline = {
+        "bound": "issue", "kernel": "fs_rollout_kernel",
+        "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
+        "frac": achieved / issue_peak, "traffic": None,
+        "peak_source": "SMs x 4 schedulers x sm_max_mhz (%s)" %
+                       ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "nvidia-smi"),
+        "rollout_kernel_ms_per_step": rollout_ms, "advance_kernel_ms_per_step": advance_ms,
+        "rollout_kernel_share_of_step": rollout_ms / (rollout_ms + advance_ms),
+        "launches_per_step": {"rollout": n_depths * len(by_class), "advance": n_depths * len(by_class)},
+        "avg_rollout_launch_ms": rollout_ms / max(n_depths * len(by_class), 1),
+        "placements_executed_per_step": float(res_p["placements_executed"].sum()),
+        "placements_per_s_kernel": float(res_p["placements_executed"].sum()) / (rollout_ms / 1e3),
+        "inst_per_placement": {k: INST_PER_PLACEMENT.get(k, INST_PER_PLACEMENT_DEFAULT) for k in by_class},
+        "hbm": {"algorithmic_gbs": algo_bytes / (rollout_ms / 1e3) / 1e9, "peak_gbs": hbm_peak,
+                "frac": algo_bytes / (rollout_ms / 1e3) / 1e9 / hbm_peak},
+    }
+
+    # ---- end to end through the one-shot C-ABI call with host buffers --------------
+    e2e = None
+    if not a.no_e2e:
+        h2d = (batch["tiles"].nbytes + batch["rows"].nbytes + batch["cols"].nbytes +
+               batch["n_entries"].nbytes + streams.nbytes)
+        d2h = P * (56 + (batch["tiles"].shape[1] // 2 + 2) * 2 + (batch["tiles"].shape[1] // 2) * 4)
+        for _ in range(2):
+            eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], a.n_sim,
+                            strat, a.seed, streams)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        e2e_rollouts = 0.0
+        for _ in range(a.steps):
+            r = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"],
+                                a.n_sim, strat, a.seed, streams)
+            e2e_rollouts += float(r["rollouts"].sum())
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        rr = torch.tensor([e2e_rollouts], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+        e2e = {"value": float(rr.item()) / float(tt.item()), "unit": "rollouts/s",
+               "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+               "ms_per_step": 1e3 * float(tt.item()) / a.steps,
+               "api": "bp_flat_search (create + upload + all depths + download + destroy)"}
+
+    # ---- strong scaling: the single 1000-problem set split over the ranks ----------
+    strong = None
+    if not a.no_strong:
+        mine = list(range(rank, P, world))
+        sub = datasets.batch_arrays([problems[i] for i in mine])
+        s2 = eng.search(sub["rows"], sub["cols"], sub["tiles"], sub["n_entries"], a.n_sim, strat,
+                        a.seed, np.asarray(mine, dtype=np.uint32))
+        for _ in range(2):
+            s2.reset()
+            s2.run()
+        barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(a.steps):
+            s2.reset()
+            s2.run()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        barrier()
+        r2 = s2.results()
+        tt = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        cc = torch.tensor([float(r2["rollouts"].sum()), float(r2["solution_found"].sum())],
+                          dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            dist.all_reduce(cc, op=dist.ReduceOp.SUM)
+        sset = float(tt.item()) / 1e3 / a.steps
+        strong = {"wall_s_full_set": sset, "rollouts_per_s": float(cc[0].item()) / sset,
+                  "solved": int(cc[1].item()), "problems": P, "partition": "problem i -> rank i mod N"}
+        s2.close()
+
+    # ---- CPU baseline beside it (rank 0, N = 1 only) --------------------------------
+    cpu = None
+    if rank == 0 and world == 1 and a.cpu_budget > 0:
+        try:
+            base = run_cpu_baseline(a, a.cpu_budget, c_problems=8)
+            pp = base["python_port"]
+            cpu = {"value": pp["rollouts_per_s"], "unit": "rollouts/s", "cores": pp["cores"],
+                   "kind": "port",
+                   "sample": "python/numpy restatement of reference CustomMCTS.predict, %d "
+                             "single-threaded processes, problems in order, first %.0f s"
+                             % (pp["cores"], a.cpu_budget),
+                   "placements_per_s": pp["placements_per_s"], "cpu_model": base["cpu_model"],
+                   "c_port_value": base["c_port"]["rollouts_per_s"],
+                   "c_port_sample": "scalar C restatement, %d pthreads, first 8 problems"
+                                    % base["c_port"]["cores"]}
+        except Exception as exc:  # the baseline is reported, never required
+            cpu = {"error": str(exc)[:300]}
+
+    if rank == 0:
+        line = {
+            "metric": "mcts_rollouts_per_s", "value": value, "unit": "rollouts/s",
+            "n_gpus": world, "steps": a.steps, "warmup": max(a.warmup, 3),
+            "ms_per_step": 1e3 * sec_per_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "u32", "data": "reference problem set (bundled npz)",
+            "config": workload_config(a),
+            "rollouts_per_step": rollouts, "placements_per_step": placements,
+            "rollouts_executed_per_step": rollouts_exec,
+            "placements_executed_per_step": placements_exec,
+            "placements_per_s": placements / sec_per_step,
+            "rollouts_executed_per_s": rollouts_exec / sec_per_step,
+            "solved": int(solved), "solutions_verified": verified,
+            "problems_per_step": P * world, "wall_s_per_step": wall / a.steps,
+            "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": roofline, "e2e": e2e, "strong": strong, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line))
+    search.close()
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse_args()
+    if a.impl == "reference":
+        reference_arm(a)
+    else:
+        our_arm(a)
+
+
+if __name__ == "__main__":
+    main()

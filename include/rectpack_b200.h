@@ -124,6 +124,7 @@ typedef struct {
     int64_t rollouts;            /* perform_simulation calls the reference would make     */
     int64_t rollout_placements;  /* placements inside those rollouts                      */
     int64_t rollouts_executed;   /* rollouts the device ran (no early exit inside a depth)*/
+    int64_t placements_executed; /* placements inside the rollouts the device ran         */
 } bp_search_result;
 
 /* Problems of mixed shapes in one batch.
@@ -142,6 +143,11 @@ int bp_search_create(bp_context *ctx, int n_problems, const int32_t *rows, const
 int bp_search_set_partition(bp_search *s, int rank, int n_ranks, int sim_begin, int n_local);
 /* (re)load the initial states into HBM; must precede bp_search_run */
 int bp_search_reset(bp_search *s);
+/* on != 0: bracket every depth's rollout and advance launches with CUDA events on the
+ * context's stream.  bp_search_profile synchronises and returns the milliseconds spent in
+ * the rollout kernels and in the advance kernels of the last run, over n_depths depths. */
+int bp_search_set_profiling(bp_search *s, int on);
+int bp_search_profile(bp_search *s, double *rollout_ms, double *advance_ms, int *n_depths);
 /* run every depth on the context's stream; asynchronous; single rank only */
 int bp_search_run(bp_search *s);
 /* stepwise form (root-parallel): for depth d = 0, 1, ... until bp_search_max_depth:

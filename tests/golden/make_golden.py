@@ -15,7 +15,7 @@ occupancy fix, Philox stream injected at binpack/MCTS.py:174) and records:
                      solution_tiles_order, every child's score)
   alpha_game.json    Board/BinPackGame walks: valid masks, add_tile, win state
   puct.json          MCTS.getActionProb with a deterministic stub net
-  problems_*.npz     the reference's problem sets in a compact binary form
+  visapi_b200/data/problems_*.npz   the reference's problem sets, compact binary form
   published.json     aggregates of csv_results/results_{g,b}.csv
 
 Nothing here is read at test time from /root/reference; the fixtures are committed.
@@ -97,7 +97,7 @@ def write_npz(name, probs):
         n_tiles[i] = len(p[2])
         tiles[i, :len(p[2])] = np.array(p[2], np.uint8)
     ids = np.array([str(p[3]) for p in probs])
-    path = os.path.join(HERE, name)
+    path = os.path.join(ROOT, "visapi_b200", "data", name)
     np.savez_compressed(path, rows=rows, cols=cols, tiles=tiles, n_tiles=n_tiles, ids=ids)
     print("wrote %s (%d bytes)" % (name, os.path.getsize(path)))
 

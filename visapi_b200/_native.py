@@ -30,7 +30,8 @@ class EngineError(RuntimeError):
 class SearchResult(C.Structure):
     _fields_ = [("depth", C.c_int32), ("solution_found", C.c_int32), ("score", C.c_int32),
                 ("n_order", C.c_int32), ("n_tiles_placed", C.c_int64), ("rollouts", C.c_int64),
-                ("rollout_placements", C.c_int64), ("rollouts_executed", C.c_int64)]
+                ("rollout_placements", C.c_int64), ("rollouts_executed", C.c_int64),
+                ("placements_executed", C.c_int64)]
 
 
 _lib = None
@@ -57,6 +58,9 @@ SYMBOLS = [
                                    C.c_int, _u32, C.POINTER(_vp)]),
     ("bp_search_set_partition", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("bp_search_reset", C.c_int, [_vp]),
+    ("bp_search_set_profiling", C.c_int, [_vp, C.c_int]),
+    ("bp_search_profile", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                    C.POINTER(C.c_int)]),
     ("bp_search_run", C.c_int, [_vp]),
     ("bp_search_step_rollouts", C.c_int, [_vp]),
     ("bp_search_step_reduce", C.c_int, [_vp]),
@@ -293,7 +297,7 @@ def _results_dict(res, order, path, scores):
     a = np.frombuffer(res, dtype=np.dtype([
         ("depth", "<i4"), ("solution_found", "<i4"), ("score", "<i4"), ("n_order", "<i4"),
         ("n_tiles_placed", "<i8"), ("rollouts", "<i8"), ("rollout_placements", "<i8"),
-        ("rollouts_executed", "<i8")])).copy()
+        ("rollouts_executed", "<i8"), ("placements_executed", "<i8")])).copy()
     out = {k: a[k] for k in a.dtype.names}
     out["order"] = order
     out["path"] = path
@@ -331,6 +335,15 @@ class Search(object):
 
     def run(self):
         self.engine._check(self._lib.bp_search_run(self._h))
+
+    def set_profiling(self, on=True):
+        self.engine._check(self._lib.bp_search_set_profiling(self._h, int(bool(on))))
+
+    def profile(self):
+        """(rollout_ms, advance_ms, n_depths) of the last run; synchronises."""
+        r, a, n = C.c_double(), C.c_double(), C.c_int()
+        self.engine._check(self._lib.bp_search_profile(self._h, C.byref(r), C.byref(a), C.byref(n)))
+        return r.value, a.value, n.value
 
     def step_rollouts(self):
         self.engine._check(self._lib.bp_search_step_rollouts(self._h))

@@ -66,6 +66,7 @@ struct SearchParams {
     unsigned long long* rollouts;
     unsigned long long* rollout_placements;
     unsigned long long* rollouts_executed;
+    unsigned long long* placements_executed;
     uint16_t* prev_tile;
     int* n_order;
     uint8_t* order;          // [P][ES/2+2][2]
@@ -292,7 +293,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
         }
 
         // ---- what the reference would have counted (MCTS.py:60,76,134-140) -------
-        long long roll = 0, plc = 0;
+        long long roll = 0, plc = 0, plc_exec = 0;
         int best_score = -1, best_entry = -1;
         int* scores = p.child_scores + ((size_t)prob * (p.es / 2) + depth) * p.es;
 #pragma unroll
@@ -301,6 +302,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
             const bool is_child = (legal[j] >> lane) & 1u;
             int score = -1;
             if (is_child) {
+                plc_exec += st[j].sum_steps;
                 if (first_child < 0 || e < first_child) {
                     roll += p.n_sim;
                     plc += st[j].sum_steps;
@@ -323,7 +325,9 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
         }
         roll = warp_sum_ll(roll);
         plc = warp_sum_ll(plc);
+        plc_exec = warp_sum_ll(plc_exec);
         if (lane == 0) {
+            p.placements_executed[prob] += (unsigned long long)plc_exec;
             p.rollouts[prob] += (unsigned long long)roll;
             p.rollout_placements[prob] += (unsigned long long)plc;
             p.n_tiles_placed[prob] += (unsigned long long)plc;
@@ -445,8 +449,15 @@ struct bp_search {
     int grid_rollout[N_CLASSES] = {0};
     int* d_cls_problems = nullptr;
     ProblemDesc* d_desc = nullptr;
+    uint32_t* d_init_occ = nullptr;            // initial boards (NULL: empty boards)
+    uint8_t* d_init_tiles = nullptr;           // initial tile tables
     std::vector<void*> allocs;
     size_t counters_bytes = 0;
+    // optional per-depth CUDA-event timing of the rollout and advance launches
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;               // 3 per depth: before rollouts, between, after advance
+    int ev_depths = 0;
+    ~bp_search() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
 };
 
 template <typename T>
@@ -563,6 +574,9 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
     TRY(dev_alloc(s, &p.rollouts, P));
     TRY(dev_alloc(s, &p.rollout_placements, P));
     TRY(dev_alloc(s, &p.rollouts_executed, P));
+    TRY(dev_alloc(s, &p.placements_executed, P));
+    TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
+    if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
     TRY(dev_alloc(s, &p.prev_tile, P));
     TRY(dev_alloc(s, &p.n_order, P));
     TRY(dev_alloc(s, &p.order, P * (p.es / 2 + 2) * 2));
@@ -580,6 +594,11 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
                             cudaMemcpyHostToDevice, ctx->stream));
     BP_CUDA(cudaMemcpyAsync(s->d_cls_problems, cls_problems.data(), cls_problems.size() * sizeof(int),
                             cudaMemcpyHostToDevice, ctx->stream));
+    BP_CUDA(cudaMemcpyAsync(s->d_init_tiles, s->h_tiles.data(), P * p.es * 2, cudaMemcpyHostToDevice,
+                            ctx->stream));
+    if (boards)
+        BP_CUDA(cudaMemcpyAsync(s->d_init_occ, s->h_boards.data(), P * p.rs * p.ws * 4,
+                                cudaMemcpyHostToDevice, ctx->stream));
     BP_CUDA(cudaStreamSynchronize(ctx->stream));
 
     // persistent grid per class: every SM filled to the occupancy limit of that kernel
@@ -640,17 +659,19 @@ int bp_search_reset(bp_search* s)
     BP_CUDA(cudaSetDevice(ctx->device));
     const size_t P = p.n_problems;
     cudaStream_t st = ctx->stream;
-    if (s->h_boards.empty())
+    // the initial states are resident in HBM (uploaded by bp_search_create)
+    if (!s->d_init_occ)
         BP_CUDA(cudaMemsetAsync(p.occ, 0, P * p.rs * p.ws * 4, st));
     else
-        BP_CUDA(cudaMemcpyAsync(p.occ, s->h_boards.data(), P * p.rs * p.ws * 4, cudaMemcpyHostToDevice, st));
-    BP_CUDA(cudaMemcpyAsync(p.tiles, s->h_tiles.data(), P * p.es * 2, cudaMemcpyHostToDevice, st));
+        BP_CUDA(cudaMemcpyAsync(p.occ, s->d_init_occ, P * p.rs * p.ws * 4, cudaMemcpyDeviceToDevice, st));
+    BP_CUDA(cudaMemcpyAsync(p.tiles, s->d_init_tiles, P * p.es * 2, cudaMemcpyDeviceToDevice, st));
     BP_CUDA(cudaMemsetAsync(p.status, 0, P * sizeof(int), st));
     BP_CUDA(cudaMemsetAsync(p.depth, 0, P * sizeof(int), st));
     BP_CUDA(cudaMemsetAsync(p.n_tiles_placed, 0, P * 8, st));
     BP_CUDA(cudaMemsetAsync(p.rollouts, 0, P * 8, st));
     BP_CUDA(cudaMemsetAsync(p.rollout_placements, 0, P * 8, st));
     BP_CUDA(cudaMemsetAsync(p.rollouts_executed, 0, P * 8, st));
+    BP_CUDA(cudaMemsetAsync(p.placements_executed, 0, P * 8, st));
     BP_CUDA(cudaMemsetAsync(p.prev_tile, 0, P * 2, st));
     BP_CUDA(cudaMemsetAsync(p.n_order, 0, P * sizeof(int), st));
     BP_CUDA(cudaMemsetAsync(p.order, 0, P * (p.es / 2 + 2) * 2, st));
@@ -661,7 +682,39 @@ int bp_search_reset(bp_search* s)
     launch_advance<true>(s, 0, nullptr);
     BP_CUDA(cudaGetLastError());
     s->cur_depth = 0;
+    s->ev_depths = 0;
     s->ready = true;
+    return BP_OK;
+}
+
+int bp_search_set_profiling(bp_search* s, int on)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    s->profiling = on != 0;
+    if (s->profiling && s->ev.empty()) {
+        s->ev.resize((size_t)3 * (s->max_depth + 1));
+        for (cudaEvent_t& e : s->ev) BP_CUDA(cudaEventCreate(&e));
+    }
+    return BP_OK;
+}
+
+int bp_search_profile(bp_search* s, double* rollout_ms, double* advance_ms, int* n_depths)
+{
+    BP_REQUIRE(s && rollout_ms && advance_ms && n_depths, "null argument");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    BP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    double r = 0.0, a = 0.0;
+    for (int d = 0; d < s->ev_depths; ++d) {
+        float ms = 0.f;
+        BP_CUDA(cudaEventElapsedTime(&ms, s->ev[3 * d], s->ev[3 * d + 1]));
+        r += ms;
+        BP_CUDA(cudaEventElapsedTime(&ms, s->ev[3 * d + 1], s->ev[3 * d + 2]));
+        a += ms;
+    }
+    *rollout_ms = r;
+    *advance_ms = a;
+    *n_depths = s->ev_depths;
     return BP_OK;
 }
 
@@ -673,6 +726,7 @@ int bp_search_step_rollouts(bp_search* s)
         return BP_ERR_STATE;
     }
     BP_CUDA(cudaSetDevice(s->ctx->device));
+    if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth], s->ctx->stream));
     for (int c : s->classes) {
         dispatch_class(c, [&](auto R, auto Wc, auto E) {
             fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
@@ -682,6 +736,7 @@ int bp_search_step_rollouts(bp_search* s)
         s->ctx->launches++;
     }
     BP_CUDA(cudaGetLastError());
+    if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth + 1], s->ctx->stream));
     return BP_OK;
 }
 
@@ -715,6 +770,10 @@ int bp_search_step_commit(bp_search* s, const void* gathered_stats_dev)
     BP_CUDA(cudaSetDevice(s->ctx->device));
     launch_advance<false>(s, s->cur_depth + 1, static_cast<const ChildStats*>(gathered_stats_dev));
     BP_CUDA(cudaGetLastError());
+    if (s->profiling) {
+        BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth + 2], s->ctx->stream));
+        s->ev_depths = s->cur_depth + 1;
+    }
     s->cur_depth += 1;
     return BP_OK;
 }
@@ -759,7 +818,7 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
     BP_CUDA(cudaSetDevice(ctx->device));
     const size_t P = p.n_problems;
     std::vector<int> status(P), depth(P), n_order(P);
-    std::vector<unsigned long long> ntp(P), roll(P), plc(P), exe(P);
+    std::vector<unsigned long long> ntp(P), roll(P), plc(P), exe(P), pexe(P);
     cudaStream_t st = ctx->stream;
     BP_CUDA(cudaMemcpyAsync(status.data(), p.status, P * 4, cudaMemcpyDeviceToHost, st));
     BP_CUDA(cudaMemcpyAsync(depth.data(), p.depth, P * 4, cudaMemcpyDeviceToHost, st));
@@ -768,6 +827,7 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
     BP_CUDA(cudaMemcpyAsync(roll.data(), p.rollouts, P * 8, cudaMemcpyDeviceToHost, st));
     BP_CUDA(cudaMemcpyAsync(plc.data(), p.rollout_placements, P * 8, cudaMemcpyDeviceToHost, st));
     BP_CUDA(cudaMemcpyAsync(exe.data(), p.rollouts_executed, P * 8, cudaMemcpyDeviceToHost, st));
+    BP_CUDA(cudaMemcpyAsync(pexe.data(), p.placements_executed, P * 8, cudaMemcpyDeviceToHost, st));
     if (order)
         BP_CUDA(cudaMemcpyAsync(order, p.order, P * (p.es / 2 + 2) * 2, cudaMemcpyDeviceToHost, st));
     if (path)
@@ -786,6 +846,7 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
         r.rollouts = (int64_t)roll[i];
         r.rollout_placements = (int64_t)plc[i];
         r.rollouts_executed = (int64_t)exe[i];
+        r.placements_executed = (int64_t)pexe[i];
     }
     return BP_OK;
 }
