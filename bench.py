@@ -35,10 +35,19 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-# warp instructions per placement of the rollout kernel, per shape class (RHO, W, EJ);
-# frozen from ncu smsp__inst_executed.sum / placements (profiles/)
-INST_PER_PLACEMENT = {}
-INST_PER_PLACEMENT_DEFAULT = 150.0
+
+
+def model_inst_per_placement(key):
+    """ALGORITHMIC warp instructions per placement for shape class "RHO,W,EJ": the
+    warp-per-board work model of SURVEY.md 8(d), frozen in DESIGN.md section 5 before any
+    kernel tuning (LFB 4+2*RHO*W, free run 4*W, legality 6*EJ, Philox+reduce 27,
+    k-th-set select 6*EJ, place 6*RHO*W, pair removal 6, loop 6)."""
+    rho, w, ej = (int(v) for v in key.split(","))
+    return float((4 + 2 * rho * w) + 4 * w + 6 * ej + 27 + 6 * ej + 6 * rho * w + 6 + 6)
+
+
+# raw ncu smsp__inst_executed.sum / placements of the round-1 v1 kernel (profiles/r1/)
+MEASURED_INST_PER_PLACEMENT_V1 = {"1,1,2": 137.2, "1,2,2": 167.4, "2,1,2": 148.9, "2,2,2": 182.1}
 
 
 def parse_args():
@@ -278,7 +287,7 @@ def our_arm(a):
     for k, pe in zip(keys, res_p["placements_executed"].tolist()):
         by_class[k] = by_class.get(k, 0) + pe
     for k, pe in by_class.items():
-        algo_inst += pe * INST_PER_PLACEMENT.get(k, INST_PER_PLACEMENT_DEFAULT)
+        algo_inst += pe * model_inst_per_placement(k)
     info = eng.device_info()
     peaks = {}
     try:
@@ -305,7 +314,8 @@ def our_arm(a):
         "avg_rollout_launch_ms": rollout_ms / max(n_depths * len(by_class), 1),
         "placements_executed_per_step": float(res_p["placements_executed"].sum()),
         "placements_per_s_kernel": float(res_p["placements_executed"].sum()) / (rollout_ms / 1e3),
-        "inst_per_placement": {k: INST_PER_PLACEMENT.get(k, INST_PER_PLACEMENT_DEFAULT) for k in by_class},
+        "algorithmic_inst_per_placement": {k: model_inst_per_placement(k) for k in by_class},
+        "ncu_inst_per_placement_r1_v1": {k: MEASURED_INST_PER_PLACEMENT_V1.get(k) for k in by_class},
         "hbm": {"algorithmic_gbs": algo_bytes / (rollout_ms / 1e3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": algo_bytes / (rollout_ms / 1e3) / 1e9 / hbm_peak},
     }
