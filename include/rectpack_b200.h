@@ -179,6 +179,34 @@ int bp_flat_search(bp_context *ctx, int n_problems, const int32_t *rows, const i
                    uint32_t seed, bp_search_result *results, uint8_t *order, int32_t *path,
                    int32_t *child_scores);
 
+/* ---- a15 + a16: PUCT tree search (MCTS.search / getActionProb, MCTS.py:204-335) -- */
+/* n_trees independent trees of one shape searched in lock step, one warp per tree.
+ * Nodes are keyed by the exact (board, tile list) state, like the reference's string
+ * keys, so transpositions share statistics.  A tree keeps its nodes across
+ * bp_tree_set_root calls (the reference keeps its dicts for a whole episode) until
+ * bp_tree_reset.  One simulation of every tree:
+ *   bp_tree_select  walks root -> leaf/terminal with argmax UCB (float64, lowest action
+ *                   wins ties).  out_status[i] = 0: tree i stopped at an unexpanded leaf
+ *                   whose board, padded tile list and valid-action mask are returned for
+ *                   nnet.predict; 1: it stopped at a terminal node (nothing to evaluate).
+ *   bp_tree_backup  priors[i][a] = the leaf's policy already masked with the valid moves
+ *                   and normalised (MCTS.py:281-292, done by the caller next to the net),
+ *                   values[i] = the net's v; both ignored for trees with status 1.
+ *                   Updates Qsa/Nsa/Ns along each path (:326-334); out_values (nullable)
+ *                   receives the v each search() call returns.                          */
+int bp_tree_create(bp_context *ctx, int n_trees, int rows, int cols, int n_entries,
+                   int max_nodes, double cpuct, bp_tree **out);
+int bp_tree_reset(bp_tree *t);
+int bp_tree_set_root(bp_tree *t, const uint32_t *occ, const uint8_t *tiles);
+int bp_tree_select(bp_tree *t, uint32_t *out_leaf_occ, uint8_t *out_leaf_tiles,
+                   uint8_t *out_valid, int32_t *out_status);
+int bp_tree_backup(bp_tree *t, const double *priors, const double *values, double *out_values);
+/* counts[i][a] = Nsa[(root_i, a)]; n_nodes (nullable)[i] = nodes in tree i */
+int bp_tree_root_counts(bp_tree *t, int32_t *counts, int32_t *n_nodes);
+/* same counts left on the device (int32[n_trees][n_entries]) for an NCCL all-reduce */
+int bp_tree_root_counts_dev(bp_tree *t, void **counts_dev, int64_t *n_bytes);
+int bp_tree_destroy(bp_tree *t);
+
 #ifdef __cplusplus
 }
 #endif

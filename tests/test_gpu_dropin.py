@@ -1,0 +1,279 @@
+"""The reference-facing Python surface (SolutionChecker, State, CustomMCTS, BinPackGame,
+MCTS) against the reference's own unit-test vectors and the reference-made fixtures.
+Everything here runs the CUDA path: marked gpu."""
+import numpy as np
+import pytest
+
+from tests import reference_vectors as rv
+from tests.conftest import board_from_hex, hex_rows_of
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def SC():
+    from visapi_b200.solution_checker import SolutionChecker
+    return SolutionChecker
+
+
+def _state(board, tiles):
+    from visapi_b200.state import State
+    return State(np.array(board), tiles)
+
+
+# ---- the reference's engine/test_solution_checker.py cases, same calls ----------------
+def test_get_next_lfb_on_grid(SC):
+    for board, want in rv.LFB:
+        assert SC.get_next_lfb_on_grid(np.array(board)) == want
+
+
+def test_get_next_turn_copy_destroy_only_success(SC):
+    st = _state(rv.NEXT_TURN_BOARD, rv.NEXT_TURN_TILES)
+    success, new_board = SC.get_next_turn(st, rv.NEXT_TURN_TILE, val=1, get_only_success=False,
+                                          destroy_state=False)
+    assert success is True
+    np.testing.assert_array_equal(new_board, np.array(rv.NEXT_TURN_AFTER))
+    np.testing.assert_array_equal(st.board, np.array(rv.NEXT_TURN_BOARD))
+    success, new_board = SC.get_next_turn(st, rv.NEXT_TURN_TILE, val=1, destroy_state=True)
+    assert success is True
+    np.testing.assert_array_equal(st.board, new_board)
+    st = _state(rv.NEXT_TURN_BOARD, rv.NEXT_TURN_TILES)
+    success, new_board = SC.get_next_turn(st, rv.NEXT_TURN_TILE, val=1, get_only_success=True,
+                                          destroy_state=True)
+    assert success is True and new_board is None
+
+
+def test_get_next_turn_sentinels(SC):
+    from visapi_b200 import solution_checker as m
+    full = np.ones((2, 2))
+    assert SC.get_next_turn(_state(full, []), (1, 1))[0] == m.ALL_TILES_USED
+    assert SC.get_next_turn(_state(full, [(1, 1), (1, 1)]), (1, 1))[0] == m.NO_NEXT_POSITION_TILES_UNUSED
+    st = _state(rv.NEXT_TURN_BOARD, rv.NEXT_TURN_TILES)
+    assert SC.get_next_turn(st, (1, 2)) == (m.TILE_CANNOT_BE_PLACED, None)
+    assert SC.get_next_turn(st, (3, 1)) == (m.TILE_CANNOT_BE_PLACED, None)
+
+
+def test_get_valid_next_moves(SC):
+    for board, tiles, do_sort, want in rv.VALID_MOVES:
+        tl = rv.sort_tiles(tiles) if do_sort else tiles
+        st = _state(board, tl)
+        assert SC.get_valid_next_moves(st, tl) == want
+        assert SC.get_valid_next_moves(st, tl, colorful_states=True) == want
+    with pytest.raises(TypeError):
+        SC.get_valid_next_moves(_state(np.ones((2, 2)), [(1, 1)]), [(1, 1)])
+
+
+def test_colorful_vs_plain_occupancy(SC):
+    """a cell painted 2 is free for the '== 1' rule and occupied for the colorful rule"""
+    board = np.array([[1, 1, 1, 1], [0, 0, 2, 0], [0, 0, 0, 0]])
+    tiles = [(1, 1), (1, 2), (1, 3), (1, 4)]
+    st = _state(board, tiles)
+    assert SC.get_valid_next_moves(st, tiles, colorful_states=True) == [(1, 1), (1, 2)]
+    assert SC.get_valid_next_moves(st, tiles, colorful_states=False) == tiles
+    assert SC.get_next_occupied_col(board, (1, 0), colorful_states=True) == 2
+    assert SC.get_next_occupied_col(board, (1, 0), colorful_states=False) == 4
+    ok, _ = SC.place_element_on_grid_given_grid((1, 3), (1, 0), 5, board.copy(), 4, 3)
+    assert ok is True
+    ok, g = SC.place_element_on_grid_given_grid((1, 3), (1, 0), 5, board.copy(), 4, 3,
+                                                colorful_states=True)
+    assert ok is False and g is None
+
+
+def test_eliminate_pair_tiles(SC):
+    for tiles, tile, want in rv.ELIMINATE:
+        if want is ValueError:
+            with pytest.raises(ValueError):
+                SC.eliminate_pair_tiles(list(tiles), tile_to_remove=tile)
+        else:
+            assert SC.eliminate_pair_tiles(list(tiles), tile_to_remove=tile) == want
+
+
+def test_possible_actions_and_mask(SC):
+    grid = np.array(rv.ACTION_GRID)
+    assert SC.get_possible_tile_actions_given_grid(grid, rv.POSSIBLE_TILES) == rv.POSSIBLE_EXPECTED
+    assert SC.get_valid_tile_actions_indexes_given_grid(grid, rv.MASK_TILES) == rv.MASK_EXPECTED
+    tiles, n, want = rv.PAD_CASE
+    assert SC.pad_tiles_with_zero_scalars(tiles, n) == want
+
+
+def test_find_first_module():
+    from visapi_b200 import search
+    assert search.find_first(0, np.array([1.0, 1.0, 0.0, 0.0])) == 2
+    assert search.find_first(1, np.zeros(5)) == -1
+
+
+# ---- CustomMCTS ------------------------------------------------------------------------
+def test_custom_mcts_predict_golden(golden):
+    from visapi_b200.mcts import CustomMCTS
+    from visapi_b200.verify import replay_solution
+    cases = golden("flat_search.json")
+    picked = [c for c in cases if c["solution_found"]][:3] + cases[:3] + \
+             [c for c in cases if len(c["tiles"]) > 60][:1]
+    for c in picked:
+        board = np.zeros((c["rows"], c["cols"]))
+        tiles = [tuple(t) for t in c["tiles"]]
+        m = CustomMCTS(tiles, board, strategy=c["strategy"], seed=c["seed"], stream=c["stream"])
+        root, depth, found = m.predict(N=c["n_sim"])
+        assert depth == c["depth"] and found == c["solution_found"]
+        assert m.n_tiles_placed == c["n_tiles_placed"]
+        assert [list(t) for t in m.solution_tiles_order] == c["solution_tiles_order"]
+        assert root is m.state and not board.any()
+        # the tree: one child per evaluated entry of every depth, with the golden scores
+        node, want = root, {}
+        for d, e, sc in c["children"]:
+            want.setdefault(d, []).append(sc)
+        for d in sorted(want):
+            got = [ch.score for ch in node.children]
+            exp = [(len(node.tiles) / 2 - 1) if s == "S" else s for s in want[d]]
+            assert got == exp, (c["name"], d)
+            committed = [ch for ch in node.children if ch.children or ch is node.children[0]]
+            nxt = None
+            if d < depth:
+                # follow the committed child: the one whose board leads on
+                idx = [i for i, ch in enumerate(node.children)]
+                scores = [ch.score for ch in node.children]
+                nxt = node.children[scores.index(max(scores))]
+            if nxt is None:
+                break
+            node = nxt
+        if found:
+            base = [tuple(t) for t in c["tiles"]]
+            half = []
+            pool = list(base)
+            while pool:
+                t = pool.pop(0)
+                pool.remove((t[1], t[0]))
+                half.append(t)
+            ok, why = replay_solution(c["rows"], c["cols"], half, m.solution_tiles_order)
+            assert ok, why
+
+
+def test_custom_mcts_rollout_api(golden):
+    from oracle import c_oracle
+    from visapi_b200.mcts import CustomMCTS
+    from visapi_b200.state import State
+    c = golden("flat_search.json")[0]
+    tiles = [tuple(t) for t in c["tiles"]]
+    board = np.zeros((c["rows"], c["cols"]))
+    m = CustomMCTS(tiles, board, seed=5, stream=9)
+    depth, root, order = m.perform_simulation(State(board, tiles))
+    want = c_oracle.rollout(board, tiles, 5, 9, 0, 0)
+    assert (depth == "ALL_TILES_USED") == want["solved"]
+    assert [list(t) for t in order] == want["moves"]
+    assert m.n_tiles_placed == want["placements"]
+    score, order = m.perform_simulations(State(board, tiles), N=40)
+    depths = [c_oracle.rollout(board, tiles, 5, 9, 1, s) for s in range(40)]
+    if not any(d["solved"] for d in depths):
+        assert score == max(d["steps"] for d in depths)
+
+
+def test_predict_many_matches_single(golden):
+    from visapi_b200.mcts import CustomMCTS
+    cases = [c for c in golden("flat_search.json") if c["n_sim"] == 8 and c["strategy"] == "max_depth"
+             and len(c["tiles"]) == 40]
+    probs = [([tuple(t) for t in c["tiles"]], np.zeros((c["rows"], c["cols"]))) for c in cases]
+    out = CustomMCTS.predict_many(probs, N=8, streams=[c["stream"] for c in cases])
+    for c, o in zip(cases, out):
+        assert o["depth"] == c["depth"] and o["n_tiles_placed"] == c["n_tiles_placed"]
+        assert [list(t) for t in o["solution_tiles_order"]] == c["solution_tiles_order"]
+
+
+# ---- alpha path ------------------------------------------------------------------------
+def test_binpack_game_golden(golden):
+    from visapi_b200.game import BinPackGame
+    for g in golden("alpha_game.json"):
+        h, w, n = g["height"], g["width"], g["n_tiles"]
+        game = BinPackGame(h, w, n)
+        assert game.getActionSize() == g["action_size"]
+        assert list(game.getBoardSize()) == g["board_size"]
+        board = (np.zeros([h, w]), np.array(g["init_tiles"]))
+        for st in g["steps"]:
+            assert hex_rows_of(board[0]) == st["board"]
+            assert [[int(t[0]), int(t[1])] for t in board[1]] == st["tiles"]
+            ended = game.getGameEnded(board, 1)
+            assert ended == st["ended"]
+            if st["ended"] == 0:
+                assert game.getValidMoves(board, 1).tolist() == st["valid"]
+            if "action" not in st:
+                break
+            keep = board[0].copy()
+            nxt, player, _ = game.getNextState(board, 1, st["action"])
+            np.testing.assert_array_equal(board[0], keep)       # input untouched
+            board = (nxt[0], np.array([[int(t[0]), int(t[1])] for t in nxt[1]]))
+
+
+def test_binpack_game_batched(golden):
+    from visapi_b200.game import BinPackGame
+    g = golden("alpha_game.json")[1]
+    h, w, n = g["height"], g["width"], g["n_tiles"]
+    game = BinPackGame(h, w, n)
+    boards, valid, ended, actions, after = [], [], [], [], []
+    steps = [s for s in g["steps"] if "action" in s]
+    for s in steps:
+        boards.append((board_from_hex(h, w, s["board"]), np.array(s["tiles"])))
+        valid.append(s["valid"])
+        actions.append(s["action"])
+    assert game.getValidMoves_batch(boards).tolist() == valid
+    assert not game.getGameEnded_batch(boards).any()
+    nxt, verdict = game.getNextState_batch(boards, 1, actions)
+    assert (verdict == 1).all()
+    for k, s in enumerate(steps[:-1]):
+        assert hex_rows_of(nxt[k][0]) == g["steps"][k + 1]["board"]
+        assert nxt[k][1].tolist() == g["steps"][k + 1]["tiles"]
+
+
+def _stub_predict(action_size, calls):
+    class Net(object):
+        def predict(self, grid):
+            calls.append(1)
+            filled = int(np.count_nonzero(np.asarray(grid)))
+            cells = int(np.asarray(grid).size)
+            pi = np.array([((a * 2654435761 + filled * 40503 + 12345) % 1000 + 1)
+                           for a in range(action_size)], dtype=np.float64)
+            return pi / pi.sum(), 0.5 * filled / cells
+    return Net()
+
+
+def test_puct_mcts_golden(golden):
+    """MCTS.getActionProb bit-exact against the reference run under the same stub net."""
+    from visapi_b200.game import BinPackGame
+    from visapi_b200.puct import MCTS
+    for g in golden("puct.json"):
+        h, w, n = g["height"], g["width"], g["n_tiles"]
+        game = BinPackGame(h, w, n)
+        for mv in g["moves"]:
+            board = (board_from_hex(h, w, mv["board"]), np.array(mv["tiles"]))
+            calls = []
+            m = MCTS(game, _stub_predict(2 * n, calls), {"numMCTSSims": g["num_sims"], "cpuct": g["cpuct"]})
+            probs = m.getActionProb(board, temp=1)
+            assert probs == mv["probs"]
+            assert len(calls) == mv["leaf_evals"]
+            m0 = MCTS(game, _stub_predict(2 * n, []), {"numMCTSSims": g["num_sims"], "cpuct": g["cpuct"]})
+            assert m0.getActionProb(board, temp=0) == mv["probs_temp0"]
+
+
+def test_batched_mcts_equals_single(golden):
+    from visapi_b200.puct import BatchedMCTS
+    g = golden("puct.json")[1]
+    h, w, n = g["height"], g["width"], g["n_tiles"]
+    moves = g["moves"]
+    B = len(moves)
+
+    def predict_batch(grids):
+        pis, vs = [], []
+        for grid in grids:
+            filled = int(np.count_nonzero(grid))
+            pi = np.array([((a * 2654435761 + filled * 40503 + 12345) % 1000 + 1)
+                           for a in range(2 * n)], dtype=np.float64)
+            pis.append(pi / pi.sum())
+            vs.append(0.5 * filled / grid.size)
+        return np.array(pis), np.array(vs)
+
+    bm = BatchedMCTS(h, w, 2 * n, predict_batch, g["num_sims"], g["cpuct"], B)
+    bm.set_roots(np.stack([board_from_hex(h, w, mv["board"]) for mv in moves]),
+                 np.array([mv["tiles"] for mv in moves]))
+    bm.simulate()
+    probs = bm.action_probs(temp=1)
+    for k, mv in enumerate(moves):
+        assert probs[k].tolist() == mv["probs"]
+    assert bm.leaf_batches <= g["num_sims"]

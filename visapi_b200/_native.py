@@ -71,6 +71,15 @@ SYMBOLS = [
     ("bp_search_destroy", C.c_int, [_vp]),
     ("bp_flat_search", C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int,
                                  C.c_int, _u32, _vp, _vp, _vp, _vp]),
+    ("bp_tree_create", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double,
+                                 C.POINTER(_vp)]),
+    ("bp_tree_reset", C.c_int, [_vp]),
+    ("bp_tree_set_root", C.c_int, [_vp, _vp, _vp]),
+    ("bp_tree_select", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
+    ("bp_tree_backup", C.c_int, [_vp, _vp, _vp, _vp]),
+    ("bp_tree_root_counts", C.c_int, [_vp, _vp, _vp]),
+    ("bp_tree_root_counts_dev", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    ("bp_tree_destroy", C.c_int, [_vp]),
 ]
 
 
@@ -372,6 +381,70 @@ class Search(object):
     def close(self):
         if getattr(self, "_h", None):
             self._lib.bp_search_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Tree(object):
+    """n_trees PUCT trees of one shape (bp_tree); see include/rectpack_b200.h."""
+
+    def __init__(self, engine, n_trees, rows, cols, n_entries, max_nodes, cpuct):
+        self.engine = engine
+        self._lib = engine._lib
+        self.B, self.rows, self.cols, self.E = int(n_trees), int(rows), int(cols), int(n_entries)
+        self.wpr = words_per_row(cols)
+        h = C.c_void_p()
+        engine._check(self._lib.bp_tree_create(engine._h, self.B, self.rows, self.cols, self.E,
+                                               int(max_nodes), float(cpuct), C.byref(h)))
+        self._h = h
+        self._occ = np.zeros((self.B, self.rows, self.wpr), np.uint32)
+        self._tiles = np.zeros((self.B, self.E, 2), np.uint8)
+        self._valid = np.zeros((self.B, self.E), np.uint8)
+        self._status = np.zeros(self.B, np.int32)
+
+    def reset(self):
+        self.engine._check(self._lib.bp_tree_reset(self._h))
+
+    def set_root(self, occ, tiles):
+        occ = np.ascontiguousarray(occ, dtype=np.uint32).reshape(self.B, self.rows, self.wpr)
+        tiles = np.ascontiguousarray(tiles, dtype=np.uint8).reshape(self.B, self.E, 2)
+        self.engine._check(self._lib.bp_tree_set_root(self._h, _ptr(occ), _ptr(tiles)))
+        self.engine.synchronize()      # occ/tiles are the caller's buffers
+
+    def select(self):
+        """-> (status [B], leaf occupancy [B, rows, wpr], leaf tiles [B, E, 2], valid [B, E])."""
+        self.engine._check(self._lib.bp_tree_select(self._h, _ptr(self._occ), _ptr(self._tiles),
+                                                    _ptr(self._valid), _ptr(self._status)))
+        return self._status, self._occ, self._tiles, self._valid
+
+    def backup(self, priors, values, want_values=True):
+        priors = np.ascontiguousarray(priors, dtype=np.float64).reshape(self.B, self.E)
+        values = np.ascontiguousarray(values, dtype=np.float64).reshape(self.B)
+        out = np.zeros(self.B, np.float64) if want_values else None
+        self.engine._check(self._lib.bp_tree_backup(self._h, _ptr(priors), _ptr(values), _ptr(out)))
+        if out is None:
+            self.engine.synchronize()
+        return out
+
+    def root_counts(self):
+        counts = np.zeros((self.B, self.E), np.int32)
+        n_nodes = np.zeros(self.B, np.int32)
+        self.engine._check(self._lib.bp_tree_root_counts(self._h, _ptr(counts), _ptr(n_nodes)))
+        return counts, n_nodes
+
+    def root_counts_dev(self):
+        ptr, nbytes = C.c_void_p(), C.c_int64()
+        self.engine._check(self._lib.bp_tree_root_counts_dev(self._h, C.byref(ptr), C.byref(nbytes)))
+        return ptr.value, nbytes.value
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.bp_tree_destroy(self._h)
             self._h = None
 
     def __del__(self):

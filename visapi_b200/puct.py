@@ -1,0 +1,159 @@
+"""Drop-in PUCT ``MCTS`` (reference: binpack/MCTS.py:204-335, alpha/MCTS.py:302-434).
+
+The tree lives on the device (visapi_b200/csrc/puct.cu): struct-of-arrays visit /
+value / prior tables in HBM, select and backup as kernels, nodes keyed by the exact
+(board, tile list) state exactly like the reference's string keys.  The neural net
+stays where the reference has it — ``nnet.predict`` is called by the host on every
+leaf, and its policy is masked with the valid moves and renormalised next to the call
+(MCTS.py:281-292).  ``BatchedMCTS`` advances many games in lock step and evaluates all
+their leaves as one batch.
+"""
+import numpy as np
+
+from . import runtime
+from ._native import Tree, pack_occupancy, pack_tiles, unpack_occupancy
+
+EPS = 0.1
+
+
+def _mask_and_normalise(pi, valids):
+    """Ps = Ps * valids; renormalise; uniform over valid moves when everything is masked
+    (binpack/MCTS.py:281-292)."""
+    p = np.asarray(pi, dtype=np.float64) * valids
+    total = np.sum(p)
+    if total > 0:
+        p = p / total
+    else:
+        p = p + valids
+        p = p / np.sum(p)
+    return p
+
+
+class MCTS(object):
+    """One tree.  ``args`` needs numMCTSSims and cpuct; ``args.get('maxNodes')`` bounds the
+    nodes kept across calls (default: enough for a whole episode)."""
+
+    predict_on_grid_only = True        # binpack/MCTS.py:277 passes canonicalBoard[0]
+
+    def __init__(self, game, nnet, args, device=None):
+        self.game, self.nnet, self.args = game, nnet, args
+        self.device = device
+        self.n_actions = game.getActionSize()
+        sims = int(args['numMCTSSims'] if isinstance(args, dict) else args.numMCTSSims)
+        cpuct = float(args['cpuct'] if isinstance(args, dict) else args.cpuct)
+        max_nodes = None
+        if isinstance(args, dict):
+            max_nodes = args.get('maxNodes')
+        if not max_nodes:
+            max_nodes = (sims + 2) * (self.n_actions // 2 + 2) * 2
+        self.num_sims = sims
+        h, w = game.getBoardSize()[0], game.getBoardSize()[1]
+        self.height, self.width = h, w
+        self._tree = Tree(runtime.get_engine(device), 1, h, w, self.n_actions, max_nodes, cpuct)
+        self._root_key = None
+        self.leaf_evals = 0
+
+    def _pack(self, board):
+        occ = pack_occupancy(np.asarray(board[0])[None], colorful=True)
+        tiles = pack_tiles([[(int(t[0]), int(t[1])) for t in board[1]]], self.n_actions)
+        return occ, tiles
+
+    def _set_root(self, board):
+        occ, tiles = self._pack(board)
+        key = (occ.tobytes(), tiles.tobytes())
+        if key != self._root_key:
+            self._tree.set_root(occ, tiles)
+            self._root_key = key
+
+    def search(self, canonicalBoard):
+        """One simulation from ``canonicalBoard``; returns the value propagated to it."""
+        self._set_root(canonicalBoard)
+        status, occ, tiles, valid = self._tree.select()
+        priors = np.zeros((1, self.n_actions))
+        values = np.zeros(1)
+        if status[0] == 0:
+            grid = unpack_occupancy(occ, self.width)[0].astype(np.float64)
+            if self.predict_on_grid_only:
+                pi, v = self.nnet.predict(grid)
+            else:
+                pi, v = self.nnet.predict((grid, tiles[0].astype(np.int64)))
+            self.leaf_evals += 1
+            priors[0] = _mask_and_normalise(pi, valid[0].astype(np.float64))
+            values[0] = v
+        return float(self._tree.backup(priors, values)[0])
+
+    def getActionProb(self, canonicalBoard, temp=1):
+        """numMCTSSims simulations, then the visit-count policy (MCTS.py:221-244)."""
+        for _ in range(self.num_sims):
+            self.search(canonicalBoard)
+        self._set_root(canonicalBoard)
+        counts = [int(c) for c in self._tree.root_counts()[0][0]]
+        if temp == 0:
+            best = int(np.argmax(counts))
+            probs = [0] * len(counts)
+            probs[best] = 1
+            return probs
+        counts = [x ** (1. / temp) for x in counts]
+        total = float(sum(counts))
+        return [x / total for x in counts]
+
+    def n_nodes(self):
+        return int(self._tree.root_counts()[1][0])
+
+    def reset(self):
+        self._tree.reset()
+        self._root_key = None
+
+
+class BatchedMCTS(object):
+    """B games of one shape searched in lock step; ``predict_batch(grids [B', H, W]) ->
+    (pi [B', 2n], v [B'])`` is called once per simulation on the leaves of all trees."""
+
+    def __init__(self, height, width, n_actions, predict_batch, num_sims, cpuct, n_trees,
+                 max_nodes=None, device=None):
+        self.height, self.width, self.n_actions = height, width, n_actions
+        self.predict_batch = predict_batch
+        self.num_sims, self.B = int(num_sims), int(n_trees)
+        if not max_nodes:
+            max_nodes = (self.num_sims + 2) * (n_actions // 2 + 2) * 2
+        self._tree = Tree(runtime.get_engine(device), self.B, height, width, n_actions, max_nodes,
+                          cpuct)
+        self.leaf_evals = 0
+        self.leaf_batches = 0
+
+    def set_roots(self, grids, tile_tables):
+        """grids [B, H, W] (non-zero = occupied); tile_tables [B, 2n, 2]."""
+        self._tree.set_root(pack_occupancy(np.asarray(grids), colorful=True),
+                            pack_tiles(np.asarray(tile_tables, dtype=np.uint8)))
+
+    def simulate(self, n=None):
+        for _ in range(self.num_sims if n is None else n):
+            status, occ, tiles, valid = self._tree.select()
+            priors = np.zeros((self.B, self.n_actions))
+            values = np.zeros(self.B)
+            need = np.flatnonzero(status == 0)
+            if need.size:
+                grids = unpack_occupancy(occ[need], self.width).astype(np.float32)
+                pi, v = self.predict_batch(grids)
+                pi = np.asarray(pi, dtype=np.float64)
+                for k, i in enumerate(need):
+                    priors[i] = _mask_and_normalise(pi[k], valid[i].astype(np.float64))
+                values[need] = np.asarray(v, dtype=np.float64).reshape(-1)
+                self.leaf_evals += int(need.size)
+                self.leaf_batches += 1
+            self._tree.backup(priors, values, want_values=False)
+
+    def action_probs(self, temp=1):
+        counts = self._tree.root_counts()[0].astype(np.float64)
+        if temp == 0:
+            probs = np.zeros_like(counts)
+            probs[np.arange(self.B), counts.argmax(axis=1)] = 1
+            return probs
+        c = counts ** (1. / temp)
+        return c / c.sum(axis=1, keepdims=True)
+
+    def root_counts_dev(self):
+        return self._tree.root_counts_dev()
+
+    def reset(self):
+        self._tree.reset()
