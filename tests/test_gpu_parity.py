@@ -255,3 +255,98 @@ def test_flat_search_mixed_entry_counts(eng, golden):
                           streams=[c["stream"] for c in cases], want_scores=True)
     for i, c in enumerate(cases):
         _check_flat(c, res, i, 5, "max_depth")
+
+
+def test_root_parallel_emulated_ranks(eng, golden):
+    """The rollouts of every child split over 3 'ranks' (three partitioned searches stepped
+    one after the other on one GPU, statistics concatenated rank-major) give the same
+    result, bit for bit, as the single-rank search."""
+    import torch
+    from visapi_b200 import pack_tiles
+    from visapi_b200.parallel import _DevicePointer, split_sims
+    cases = [c for c in golden("flat_search.json") if c["n_sim"] in (11, 70) and
+             c["strategy"] == "max_depth"][:6] + \
+            [c for c in golden("flat_search.json") if c["strategy"] == "avg_depth" and c["n_sim"] == 45]
+    for c in cases:
+        n_sim, strat = c["n_sim"], 0 if c["strategy"] == "max_depth" else 1
+        args = ([c["rows"]], [c["cols"]], pack_tiles([c["tiles"]]), [len(c["tiles"])], n_sim, strat,
+                123, [c["stream"]])
+        world = 3
+        searches = [eng.search(*args) for _ in range(world)]
+        for r, s in enumerate(searches):
+            b, n = split_sims(n_sim, r, world)
+            s.set_partition(r, world, b, n)
+            s.reset()
+        nbytes = searches[0].stats_buffer()[1]
+        gathered = torch.empty(world * nbytes, dtype=torch.uint8, device="cuda")
+        views = [torch.as_tensor(_DevicePointer(s.stats_buffer()[0], nbytes), device="cuda")
+                 for s in searches]
+        for _ in range(searches[0].max_depth):
+            for s in searches:
+                s.step_rollouts()
+                s.step_reduce()
+            for r in range(world):
+                gathered[r * nbytes:(r + 1) * nbytes].copy_(views[r])
+            for s in searches:
+                s.step_commit(gathered.data_ptr())
+        for s in searches:
+            res = s.results(want_scores=True)
+            _check_flat(c, res, 0, n_sim, c["strategy"])
+            s.close()
+
+
+def test_search_reset_is_repeatable(eng, golden):
+    from visapi_b200 import pack_tiles
+    c = golden("flat_search.json")[0]
+    s = eng.search([c["rows"]], [c["cols"]], pack_tiles([c["tiles"]]), [len(c["tiles"])],
+                   c["n_sim"], 0, 123, [c["stream"]])
+    s.set_profiling(True)
+    outs = []
+    for _ in range(3):
+        s.reset()
+        s.run()
+        outs.append(s.results(want_scores=True))
+    rollout_ms, advance_ms, depths = s.profile()
+    assert depths == s.max_depth and rollout_ms > 0 and advance_ms > 0
+    for o in outs:
+        _check_flat(c, o, 0, c["n_sim"], c["strategy"])
+    s.close()
+
+
+def test_argument_errors(eng):
+    import visapi_b200
+    from visapi_b200 import pack_tiles
+    with pytest.raises(visapi_b200.EngineError):
+        eng.flat_search([200], [10], pack_tiles([[(1, 1), (1, 1)]]), [2], 5)       # rows > 128
+    with pytest.raises(visapi_b200.EngineError):
+        eng.flat_search([10], [10], pack_tiles([[(1, 1), (1, 1)]]), [2], 0)        # n_sim < 1
+    with pytest.raises(ValueError):
+        eng.lfb(np.zeros((1, 4, 2), np.uint32), 20)                                # wrong words/row
+
+
+def test_full_size_properties(eng):
+    """BASELINE-size run (first 200 G problems, N = 1000): size-independent properties —
+    every reported solution replays to a full board, rollouts executed >= rollouts the
+    reference would make, unsolved problems keep score = n - depth >= 1, and the run is
+    deterministic."""
+    from visapi_b200 import datasets
+    from visapi_b200.verify import replay_solution
+    probs = datasets.load_problem_set("g")[:200]
+    batch = datasets.batch_arrays(probs)
+    r1 = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], 1000)
+    r2 = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], 1000)
+    for k in ("depth", "solution_found", "n_tiles_placed", "rollouts", "order"):
+        np.testing.assert_array_equal(r1[k], r2[k])
+    solved = 0
+    for i, p in enumerate(probs):
+        assert r1["rollouts_executed"][i] >= r1["rollouts"][i] > 0
+        if r1["solution_found"][i]:
+            solved += 1
+            ok, why = replay_solution(p.rows, p.cols, p.tiles,
+                                      r1["order"][i, :r1["n_order"][i]].tolist())
+            assert ok, (i, why)
+            assert r1["score"][i] == 0
+        else:
+            assert r1["score"][i] == 20 - r1["depth"][i] >= 1
+    # published G solve rate at N=1000/max_depth is 40.3 %; n = 200 gives +-7 points at 95 %
+    assert 0.25 <= solved / 200.0 <= 0.55

@@ -1,0 +1,87 @@
+"""Multi-GPU drivers: one process per GPU (torch.distributed), two partitionings.
+
+* instance-parallel — independent problems are dealt to ranks (problem i -> rank
+  i mod N); no collective on the data path, results are gathered on rank 0 at the end.
+* root-parallel — one (or a few) hard instances: every rank plays a contiguous slice
+  of the N rollouts of EVERY child; once per committed move the per-child statistics
+  (max depth, depth sum, first solved rollout, placements before it: 24 bytes per
+  child) are all-gathered over NCCL/NVLink and every rank takes the same first-max
+  decision.  Because each rollout owns a counter-based Philox stream, the result is
+  bit-identical to the single-GPU search for any number of ranks.
+"""
+import numpy as np
+
+CHILD_STATS_DTYPE = np.dtype([("max_steps", "<i4"), ("first_solved", "<u4"),
+                              ("sum_steps", "<i8"), ("prefix_steps", "<i8")])
+NONE_U32 = 0xFFFFFFFF
+
+
+def shard_indices(n_items, rank, world):
+    """Problem i goes to rank i mod world."""
+    return list(range(rank, n_items, world))
+
+
+def split_sims(n_sim, rank, world):
+    """Contiguous ascending slices of the n_sim rollouts: (sim_begin, n_local)."""
+    base, rem = divmod(n_sim, world)
+    begin = rank * base + min(rank, rem)
+    return begin, base + (1 if rank < rem else 0)
+
+
+def merge_child_stats(per_rank):
+    """Host statement of the merge rule the commit kernel applies to the gathered
+    statistics (visapi_b200/csrc/flat_search.cu: stats_from_gathered).  per_rank: array
+    [world, ...] of CHILD_STATS_DTYPE, rank-major, ranks holding ascending sim ranges."""
+    per_rank = np.asarray(per_rank)
+    out = np.zeros(per_rank.shape[1:], CHILD_STATS_DTYPE)
+    out["first_solved"] = NONE_U32
+    for g in range(per_rank.shape[0]):
+        r = per_rank[g]
+        out["max_steps"] = np.maximum(out["max_steps"], r["max_steps"])
+        out["sum_steps"] += r["sum_steps"]
+        open_ = out["first_solved"] == NONE_U32
+        out["prefix_steps"] = np.where(open_, out["prefix_steps"] + r["prefix_steps"],
+                                       out["prefix_steps"])
+        out["first_solved"] = np.where(open_, r["first_solved"], out["first_solved"])
+    return out
+
+
+class _DevicePointer(object):
+    """Exposes a raw device pointer through __cuda_array_interface__ (for torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (int(nbytes),), "typestr": "|u1",
+                                         "data": (int(ptr), False), "version": 2}
+
+
+def root_parallel_search(engine, batch, n_sim, strategy, seed, streams=None, group=None,
+                         want_scores=False, profile=None):
+    """Flat search of ``batch`` (datasets.batch_arrays) with the rollouts of every child split
+    over the ranks of ``group``.  Must be called by every rank, on the CUDA stream the engine
+    was given (torch's current stream).  Returns the same dict as Engine.flat_search."""
+    import torch
+    import torch.distributed as dist
+
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    search = engine.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim,
+                           strategy, seed, streams)
+    try:
+        begin, n_local = split_sims(n_sim, rank, world)
+        search.set_partition(rank, world, begin, n_local)
+        search.reset()
+        ptr, nbytes = search.stats_buffer()
+        local = torch.as_tensor(_DevicePointer(ptr, nbytes), device="cuda")
+        gathered = torch.empty(world * nbytes, dtype=torch.uint8, device=local.device)
+        for _ in range(search.max_depth):
+            search.step_rollouts()
+            search.step_reduce()
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, local, group=group)
+            else:
+                gathered.copy_(local)
+            search.step_commit(gathered.data_ptr())
+        res = search.results(want_scores=want_scores)
+    finally:
+        search.close()
+    return res
