@@ -14,11 +14,13 @@
 // A rollout never touches HBM except to read its root (once per 32 rollouts) and to
 // write 8 bytes per 32 rollouts; it is bound by instruction issue, not bandwidth.
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
 #include "board.cuh"
 #include "common.cuh"
+#include "lanes.cuh"
 
 namespace bp {
 
@@ -77,6 +79,12 @@ struct SearchParams {
     uint32_t* child_list;    // per class segments
     unsigned* child_count;   // [MAX_DEPTHS + 1][N_CLASSES]
     unsigned* task_counter;  // [MAX_DEPTHS + 1][N_CLASSES]
+    // lane-per-rollout tables of the current state of each problem (lanes.cuh)
+    int use_lanes;
+    uint32_t* planes;        // [P][8][4] bit-sliced column heights
+    EntryInfo* einfo;        // [P][ES]
+    uint32_t* wmask;         // [P][129][4] entries with w <= x
+    uint32_t* hmask;         // [P][129][4] entries with h <= y
 };
 
 __device__ __forceinline__ long long warp_sum_ll(long long v)
@@ -147,6 +155,188 @@ fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
             r.n_sims = (uint16_t)count;
             p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
         }
+    }
+}
+
+// ------------------------------------------------------- lane-per-rollout kernel
+// Same tasks and the same 8-byte record as fs_rollout_kernel, but lane i plays rollout i of
+// the chunk on its own bit-sliced board (lanes.cuh): ~25x fewer warp instructions per
+// placement.  Used when every problem starts from an empty board (skyline invariant) and
+// equal tiles are adjacent in the tile list (always true for the reference's sorted lists).
+template <int NB, int W, int EW>
+__global__ void __launch_bounds__(128)
+fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
+{
+    constexpr int WROWS = 32 * W + 1, HROWS = (1 << NB) + 1, NE = 32 * EW;
+    __shared__ uint32_t s_wmask[4][WROWS * EW];
+    __shared__ uint32_t s_hmask[4][HROWS * EW];
+    __shared__ EntryInfo s_einfo[4][NE];
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const unsigned n_children = p.child_count[depth_slot * N_CLASSES + cls];
+    const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
+    unsigned* counter = &p.task_counter[depth_slot * N_CLASSES + cls];
+    int cached_prob = -1;
+    for (;;) {
+        unsigned long long task = 0;
+        if (lane == 0) task = atomicAdd(counter, 1u);
+        task = __shfl_sync(FULLMASK, task, 0);
+        if (task >= n_tasks) break;
+        const unsigned child = (unsigned)(task / p.n_chunks);
+        const int chunk = (int)(task % p.n_chunks);
+        const uint32_t packed = p.child_list[cls_list_offset + child];
+        const int prob = (int)(packed & 0xFFFFFFu);
+        const int entry = (int)(packed >> 24);
+        const ProblemDesc d = p.desc[prob];
+        const int4 lfb = p.lfb[prob];                 // (hmin, col, run, live entries) of the parent
+
+        if (prob != cached_prob) {                    // tables of this problem's current state
+            __syncwarp();
+            const uint32_t* gw = p.wmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
+            const uint32_t* gh = p.hmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
+            for (int i = lane; i < WROWS * EW; i += 32) {
+                const int x = i / EW, q = i % EW;
+                s_wmask[warp][i] = (x <= d.cols) ? gw[x * LANES_MASK_WORDS + q] : 0u;
+            }
+            for (int i = lane; i < HROWS * EW; i += 32) {
+                const int y = i / EW, q = i % EW;
+                s_hmask[warp][i] = (y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
+            }
+            const EntryInfo* ge = p.einfo + (size_t)prob * p.es;
+            for (int i = lane; i < NE; i += 32) {
+                EntryInfo z = {0, 0, 0, 0, 0, 0, 0, 0};
+                s_einfo[warp][i] = (i < d.n_entries) ? ge[i] : z;
+            }
+            __syncwarp();
+            cached_prob = prob;
+        }
+
+        // the child: parent + entry placed at the parent's first free cell, pair removed
+        LaneBoard<NB, W, EW> s;
+        const uint32_t* gp = p.planes + (size_t)prob * LANES_PLANE_STRIDE;
+#pragma unroll
+        for (int b = 0; b < NB; ++b)
+#pragma unroll
+            for (int q = 0; q < W; ++q) s.pl[b][q] = gp[b * 4 + q];
+#pragma unroll
+        for (int q = 0; q < EW; ++q) s.alive[q] = word_range(0, lfb.w, q);
+        const EntryInfo ei = s_einfo[warp][entry];
+        uint32_t foot[W];
+#pragma unroll
+        for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + ei.w, q);
+        lanes_place(s, foot, lfb.x + ei.h);
+        kill_lowest_in_group(s.alive, ei.gs, ei.glen);
+        kill_lowest_in_group(s.alive, ei.rs, ei.rlen);
+        const int n_alive = lfb.w - 2;
+        const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
+
+        const int first = chunk * CHUNK;
+        const int count = min(CHUNK, p.n_local - first);
+        bool my_solved;
+        const int my_steps = lanes_rollout<NB, W, EW>(
+            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_einfo[warp], p.seed, d.stream, tag,
+            (uint32_t)(p.sim_begin + first + lane), lane < count, my_solved);
+
+        const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved);
+        const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
+        const int mx = __reduce_max_sync(FULLMASK, my_steps);
+        const int sum = __reduce_add_sync(FULLMASK, my_steps);
+        const int pre = __reduce_add_sync(FULLMASK, (lane <= first_lane) ? my_steps : 0);
+        if (lane == 0) {
+            ChunkRec r;
+            r.max_steps = (uint8_t)mx;
+            r.solved_lane = (uint8_t)first_lane;
+            r.sum_steps = (uint16_t)sum;
+            r.prefix_steps = (uint16_t)pre;
+            r.n_sims = (uint16_t)count;
+            p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
+        }
+    }
+}
+
+// tables the lane-per-rollout kernel reads, from the warp-per-board state of one problem
+template <int RHO, int W, int EJ>
+__device__ __forceinline__ void write_lane_tables(const SearchParams& p, int prob, const ProblemDesc& d,
+                                                  const WarpState<RHO, W, EJ>& s, int n_alive,
+                                                  uint16_t* sh_ent /* [32*EJ] */)
+{
+    const int lane = lane_id();
+    // ---- column heights, bit-sliced (every lane computes the same words) ----------------
+    uint32_t pl[8][W];
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int q = 0; q < W; ++q) pl[b][q] = 0u;
+#pragma unroll
+    for (int q = 0; q < W; ++q) {
+        for (int cb = 0; cb < 32; ++cb) {
+            int hgt = 255;                                   // padding column: never free
+            if (32 * q + cb < d.cols) {
+                hgt = d.rows;
+#pragma unroll
+                for (int k = RHO - 1; k >= 0; --k) {
+                    const uint32_t b = __ballot_sync(FULLMASK, (s.occ[k][q] >> cb) & 1u);
+                    if (b != FULLMASK) hgt = 32 * k + ctz32(~b);
+                }
+                hgt = min(hgt, d.rows);
+            }
+#pragma unroll
+            for (int b = 0; b < 8; ++b) pl[b][q] |= (uint32_t)((hgt >> b) & 1) << cb;
+        }
+    }
+    uint32_t* gp = p.planes + (size_t)prob * LANES_PLANE_STRIDE;
+#pragma unroll
+    for (int b = 0; b < 8; ++b)
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (lane == b * 4 + q) gp[lane] = (q < W) ? pl[b][q < W ? q : 0] : 0xFFFFFFFFu;
+
+    // ---- per-entry record: tile, its group of equal entries, its rotation's group -------
+    __syncwarp();
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) sh_ent[lane + 32 * j] = (uint16_t)s.ent[j];
+    __syncwarp();
+    EntryInfo* ge = p.einfo + (size_t)prob * p.es;
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) {
+        const int e = lane + 32 * j;
+        if (e < d.n_entries) {
+            EntryInfo ei = {0, 0, 0, 0, 0, 0, 0, 0};
+            const uint16_t v = sh_ent[e];
+            if (e < n_alive && v != 0) {
+                const uint16_t rot = (uint16_t)((v >> 8) | (v << 8));
+                int gs = e, ge_ = e + 1;
+                while (gs > 0 && sh_ent[gs - 1] == v) --gs;
+                while (ge_ < n_alive && sh_ent[ge_] == v) ++ge_;
+                int rs = 0, re = 0;
+                for (int i = 0; i < n_alive; ++i)
+                    if (sh_ent[i] == rot) { rs = i; re = i + 1; break; }
+                while (re > 0 && re < n_alive && sh_ent[re] == rot) ++re;
+                ei.h = (uint8_t)(v & 0xFF); ei.w = (uint8_t)(v >> 8);
+                ei.gs = (uint8_t)gs; ei.glen = (uint8_t)(ge_ - gs);
+                ei.rs = (uint8_t)rs; ei.rlen = (uint8_t)(re - rs);
+            }
+            ge[e] = ei;
+        }
+    }
+    __syncwarp();
+
+    // ---- wmask[x] = entries with w <= x, hmask[y] = entries with h <= y ------------------
+    uint32_t* gw = p.wmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
+    uint32_t* gh = p.hmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
+    for (int x = 0; x <= d.cols; ++x) {
+        uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < EJ; ++j)
+            m[j] = __ballot_sync(FULLMASK, s.ent[j] != 0u && (int)(s.ent[j] >> 8) <= x);
+        if (lane < 4) gw[x * LANES_MASK_WORDS + lane] = lane == 0 ? m[0] : (lane == 1 ? m[1] : (lane == 2 ? m[2] : m[3]));
+    }
+    for (int y = 0; y <= d.rows; ++y) {
+        uint32_t m[4] = {0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < EJ; ++j)
+            m[j] = __ballot_sync(FULLMASK, s.ent[j] != 0u && (int)(s.ent[j] & 0xFFu) <= y);
+        if (lane < 4) gh[y * LANES_MASK_WORDS + lane] = lane == 0 ? m[0] : (lane == 1 ? m[1] : (lane == 2 ? m[2] : m[3]));
     }
 }
 
@@ -423,6 +613,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
                     (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
             base += __popc(legal[j]);
         }
+        if (p.use_lanes) write_lane_tables(p, prob, d, s, n_alive, cbuf[warp]);
     }
 }
 
@@ -430,6 +621,29 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
 
 // ================================================================= host side
 using namespace bp;
+
+// lane-kernel instantiation for a warp shape class: NB height planes cover the rows of the
+// class (RHO = 1: <= 32 rows -> 6 planes, 2: <= 64 -> 7, 4: <= 128 -> 8)
+template <typename F>
+static void dispatch_lanes(int cls, F&& f)
+{
+    const int ej = cls % 3, w = (cls / 3) % 3, rho = cls / 9;
+    auto with_ew = [&](auto NBc, auto Wc) {
+        if (ej <= 1) f(NBc, Wc, IC<2>{}); else f(NBc, Wc, IC<4>{});
+    };
+    auto with_w = [&](auto NBc) {
+        switch (w) {
+            case 0: with_ew(NBc, IC<1>{}); break;
+            case 1: with_ew(NBc, IC<2>{}); break;
+            default: with_ew(NBc, IC<4>{}); break;
+        }
+    };
+    switch (rho) {
+        case 0: with_w(IC<6>{}); break;
+        case 1: with_w(IC<7>{}); break;
+        default: with_w(IC<8>{}); break;
+    }
+}
 
 struct bp_search {
     bp_context* ctx = nullptr;
@@ -447,6 +661,7 @@ struct bp_search {
     int cls_prob_off[N_CLASSES] = {0};          // offset into d_cls_problems
     int cls_list_off[N_CLASSES] = {0};          // offset into child_list
     int grid_rollout[N_CLASSES] = {0};
+    int grid_lanes[N_CLASSES] = {0};
     int* d_cls_problems = nullptr;
     ProblemDesc* d_desc = nullptr;
     uint32_t* d_init_occ = nullptr;            // initial boards (NULL: empty boards)
@@ -559,6 +774,24 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
         }
     }
 
+    // lane-per-rollout kernel: needs the skyline invariant (empty initial boards) and equal
+    // tiles adjacent in every tile list; BP_ROLLOUT=warp forces the warp-per-board kernel
+    bool lanes_ok = boards == nullptr;
+    if (const char* env = getenv("BP_ROLLOUT")) lanes_ok = lanes_ok && strcmp(env, "warp") != 0;
+    for (int i = 0; i < n_problems && lanes_ok; ++i) {
+        const uint8_t* t = tiles + (size_t)i * entry_stride * 2;
+        std::vector<int> closed;
+        int prev = -1;
+        for (int e = 0; e < n_entries[i]; ++e) {
+            const int v = t[2 * e] | (t[2 * e + 1] << 8);
+            if (v == 0 || v == prev) continue;
+            if (std::find(closed.begin(), closed.end(), v) != closed.end()) { lanes_ok = false; break; }
+            if (prev >= 0) closed.push_back(prev);
+            prev = v;
+        }
+    }
+    p.use_lanes = lanes_ok ? 1 : 0;
+
     int rc = BP_OK;
 #define TRY(x) do { rc = (x); if (rc) { bp_search_destroy(s); return rc; } } while (0)
     const size_t P = n_problems;
@@ -588,6 +821,12 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
     TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * N_CLASSES));
     TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * N_CLASSES));
     TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
+    if (p.use_lanes) {
+        TRY(dev_alloc(s, &p.planes, P * LANES_PLANE_STRIDE));
+        TRY(dev_alloc(s, &p.einfo, P * p.es));
+        TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+        TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+    }
     TRY(alloc_records(s));
 #undef TRY
     BP_CUDA(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc),
@@ -610,6 +849,16 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
                 128, 0);
         });
         s->grid_rollout[c] = ctx->sm_count * std::max(per_sm, 1);
+        if (p.use_lanes) {
+            int per_sm_l = 1;
+            dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &per_sm_l,
+                    fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>,
+                    128, 0);
+            });
+            s->grid_lanes[c] = ctx->sm_count * std::max(per_sm_l, 1);
+        }
     }
     *out = s;
     return BP_OK;
@@ -728,11 +977,18 @@ int bp_search_step_rollouts(bp_search* s)
     BP_CUDA(cudaSetDevice(s->ctx->device));
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth], s->ctx->stream));
     for (int c : s->classes) {
-        dispatch_class(c, [&](auto R, auto Wc, auto E) {
-            fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
-                <<<s->grid_rollout[c], 128, 0, s->ctx->stream>>>(s->p, c, s->cls_list_off[c],
-                                                                 s->cur_depth);
-        });
+        if (s->p.use_lanes)
+            dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
+                fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>
+                    <<<s->grid_lanes[c], 128, 0, s->ctx->stream>>>(s->p, c, s->cls_list_off[c],
+                                                                   s->cur_depth);
+            });
+        else
+            dispatch_class(c, [&](auto R, auto Wc, auto E) {
+                fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
+                    <<<s->grid_rollout[c], 128, 0, s->ctx->stream>>>(s->p, c, s->cls_list_off[c],
+                                                                     s->cur_depth);
+            });
         s->ctx->launches++;
     }
     BP_CUDA(cudaGetLastError());

@@ -1,0 +1,225 @@
+// Lane-per-rollout playout: 32 independent rollouts of one child advance in lock step,
+// one per lane, every lane holding a whole board in registers.
+//
+// Why a second mapping.  The warp-per-board rollout (board.cuh) spends a full warp
+// instruction on work that is one scalar operation per board: ncu on
+// fs_rollout_kernel<1,1,2> shows 137 warp instructions per placement with the ALU pipe 85 %
+// and the XU pipe (POPC/FLO/BREV) 75 % busy (profiles/r1).  Here each warp instruction
+// advances 32 boards, and a placement costs ~6 warp instructions.
+//
+// Board = skyline.  Every tile is placed with its top-left corner on the row-major first
+// free cell, so each column's occupied cells are a prefix from row 0 (the reference relies on
+// this: engine/solution_checker.py:107).  A board is therefore height[c] per column, stored
+// BIT-SLICED: plane b, word q holds bit b of the heights of columns 32q..32q+31.  With that
+//   LFB            = leftmost column of minimum height: NB masked steps from the top plane
+//                    down (solution_checker.py:82-92);
+//   free run       = the run of minimum-height columns starting there (:290-305):
+//                    cand & ~(cand + colbit);
+//   place (h, w)   = set the heights of the footprint columns to hmin + h: one 3-input
+//                    logic op per plane, no loop over the tile's cells (:123);
+//   legal entries  = alive & wmask[run] & hmask[rows - hmin], two table rows prepared once per
+//                    depth by the advance kernel (:307-317);
+//   pair removal   = clear the lowest alive bit of the tile's group of equal entries and of
+//                    its rotation's group (:319-332).
+// Padding columns carry the maximum height 2^NB - 1 >= rows, so they are never free.
+//
+// The random stream, the tie rules and the results are exactly those of board.cuh::rollout;
+// tests/test_gpu_parity.py checks both against the oracle and the reference-made fixtures.
+#pragma once
+#include <cstdint>
+
+#include "board.cuh"
+
+namespace bp {
+
+// per-entry record prepared by the advance kernel (8 bytes)
+struct __align__(8) EntryInfo {
+    uint8_t h, w;          // tile (0, 0 = absent)
+    uint8_t gs, glen;      // group of entries equal to (h, w): [gs, gs + glen)
+    uint8_t rs, rlen;      // group of entries equal to (w, h)
+    uint8_t pad0, pad1;
+};
+
+constexpr int LANES_TABLE_ROWS = 129;   // wmask / hmask rows per problem in HBM (index 0..128)
+constexpr int LANES_MASK_WORDS = 4;     // words per table row in HBM (128 entries)
+constexpr int LANES_PLANE_STRIDE = 32;  // words per problem: planes[8][4]
+
+template <int NB, int W, int EW>
+struct LaneBoard {
+    uint32_t pl[NB][W];    // bit-sliced column heights
+    uint32_t alive[EW];    // live entries of the (compacted) tile list
+};
+
+// bits [lo, hi) of word q of a multi-word mask
+__device__ __forceinline__ uint32_t word_range(int lo, int hi, int q)
+{
+    const int a = max(lo - 32 * q, 0), b = min(hi - 32 * q, 32);
+    return (b > a) ? bit_range(a, b) : 0u;
+}
+
+// position of the k-th (0-based) set bit of m; k < popc(m)
+__device__ __forceinline__ int select_bit32(uint32_t m, int k)
+{
+    int pos = 0, t;
+    t = __popc(m & 0xFFFFu); if (k >= t) { k -= t; pos += 16; m >>= 16; }
+    t = __popc(m & 0xFFu);   if (k >= t) { k -= t; pos += 8;  m >>= 8; }
+    t = __popc(m & 0xFu);    if (k >= t) { k -= t; pos += 4;  m >>= 4; }
+    t = __popc(m & 0x3u);    if (k >= t) { k -= t; pos += 2;  m >>= 2; }
+    if (k >= (int)(m & 1u)) pos += 1;
+    return pos;
+}
+
+// clear the lowest set bit of (alive & group [gs, gs+glen)); returns false if the group is empty
+template <int EW>
+__device__ __forceinline__ bool kill_lowest_in_group(uint32_t (&alive)[EW], int gs, int glen)
+{
+    bool done = false;
+#pragma unroll
+    for (int q = 0; q < EW; ++q) {
+        const uint32_t m = alive[q] & word_range(gs, gs + glen, q);
+        const uint32_t low = done ? 0u : (m & (0u - m));
+        alive[q] ^= low;
+        done = done || (m != 0u);
+    }
+    return done;
+}
+
+// set the heights of columns [c, c + w) to `height` (they all had the same height before)
+template <int NB, int W, int EW>
+__device__ __forceinline__ void lanes_place(LaneBoard<NB, W, EW>& s, const uint32_t (&foot)[W], int height)
+{
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t on = ((height >> b) & 1) ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+        for (int q = 0; q < W; ++q) s.pl[b][q] = (s.pl[b][q] & ~foot[q]) | (foot[q] & on);
+    }
+}
+
+// leftmost column of minimum height: cand = columns of minimum height, hmin = that height
+template <int NB, int W, int EW>
+__device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t (&cand)[W])
+{
+#pragma unroll
+    for (int q = 0; q < W; ++q) cand[q] = 0xFFFFFFFFu;
+    int hmin = 0;
+#pragma unroll
+    for (int b = NB - 1; b >= 0; --b) {
+        uint32_t z[W];
+        uint32_t any = 0u;
+#pragma unroll
+        for (int q = 0; q < W; ++q) { z[q] = cand[q] & ~s.pl[b][q]; any |= z[q]; }
+        const bool has_zero = any != 0u;          // some candidate has bit b of its height clear
+#pragma unroll
+        for (int q = 0; q < W; ++q) cand[q] = has_zero ? z[q] : cand[q];
+        hmin |= has_zero ? 0 : (1 << b);
+    }
+    return hmin;
+}
+
+// One rollout per lane, all 32 lanes of the warp in lock step (same child, sims sim0 + lane).
+// `root` is the child state (identical in every lane).  Tables live in this warp's shared
+// memory: wmask[(x) * EW + q], hmask[(y) * EW + q], einfo[e].
+// Returns the number of placements of this lane's rollout; solved = all tiles used.
+template <int NB, int W, int EW>
+__device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, int n_alive,
+                                             const uint32_t* __restrict__ wmask,
+                                             const uint32_t* __restrict__ hmask,
+                                             const EntryInfo* __restrict__ einfo, uint32_t seed,
+                                             uint32_t stream, uint32_t tag, uint32_t sim, bool active,
+                                             bool& solved)
+{
+    int steps = 0;
+    solved = false;
+    Philox4 rnd = {0u, 0u, 0u, 0u};
+    for (int it = 0;; ++it) {
+        if ((it & 3) == 0)                                   // same iteration in every lane
+            rnd = rollout_stream_block(seed, stream, tag, sim, (uint32_t)(it >> 2));
+        if (active) {
+            if (n_alive == 0) {                              // MCTS.py:167-169
+                solved = true;
+                active = false;
+            } else {
+                uint32_t cand[W];
+                const int hmin = lanes_min(s, cand);
+                bool go = hmin < rows;                       // else: full board, tiles left
+                // first candidate column and the run of candidates that starts there
+                uint32_t foot[W];
+                int col = 0, run = 0;
+                if (W == 1) {
+                    const uint32_t colbit = cand[0] & (0u - cand[0]);
+                    const uint32_t runmask = cand[0] & ~(cand[0] + colbit);
+                    run = __popc(runmask);
+                    col = __popc(colbit - 1u);
+                } else if (W == 2) {
+                    const unsigned long long c64 =
+                        (unsigned long long)cand[0] | ((unsigned long long)cand[W > 1 ? 1 : 0] << 32);
+                    const unsigned long long colbit = c64 & (0ull - c64);
+                    const unsigned long long runmask = c64 & ~(c64 + colbit);
+                    run = __popcll(runmask);
+                    col = __popcll(colbit - 1ull);
+                } else {
+                    // first non-empty word, then the run may continue through whole words
+                    bool found = false, extending = false;
+#pragma unroll
+                    for (int q = 0; q < W; ++q) {
+                        const uint32_t cq = cand[q];
+                        if (!found) {
+                            if (cq != 0u) {
+                                found = true;
+                                const uint32_t colbit = cq & (0u - cq);
+                                const uint32_t runmask = cq & ~(cq + colbit);
+                                col = 32 * q + __popc(colbit - 1u);
+                                run = __popc(runmask);
+                                extending = (runmask >> 31) != 0u;
+                            }
+                        } else if (extending) {
+                            run += __popc(cq & ~(cq + 1u));        // trailing ones
+                            extending = (cq == 0xFFFFFFFFu);
+                        }
+                    }
+                }
+                const int hidx = max(rows - hmin, 0);
+                uint32_t legal[EW];
+                int k = 0;
+#pragma unroll
+                for (int q = 0; q < EW; ++q) {
+                    legal[q] = s.alive[q] & wmask[run * EW + q] & hmask[hidx * EW + q];
+                    k += __popc(legal[q]);
+                }
+                go = go && (k != 0);                         // MCTS.py:171-172
+                if (!go) {
+                    active = false;
+                } else {
+                    const int w4 = it & 3;
+                    const uint32_t u = w4 == 0 ? rnd.x : (w4 == 1 ? rnd.y : (w4 == 2 ? rnd.z : rnd.w));
+                    int idx = (int)__umulhi(u, (uint32_t)k);                // MCTS.py:174
+                    uint32_t m = legal[0];
+                    int base = 0;
+#pragma unroll
+                    for (int q = 1; q < EW; ++q) {
+                        const int cnt = __popc(legal[q - 1]);
+                        const bool past = (base == 32 * (q - 1)) && (idx >= cnt);
+                        idx -= past ? cnt : 0;
+                        m = past ? legal[q] : m;
+                        base = past ? 32 * q : base;
+                    }
+                    const int e = base + select_bit32(m, idx);
+                    const EntryInfo ei = einfo[e];
+                    // footprint columns [col, col + w)
+#pragma unroll
+                    for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + ei.w, q);
+                    lanes_place(s, foot, hmin + ei.h);                      // MCTS.py:175-178
+                    kill_lowest_in_group(s.alive, ei.gs, ei.glen);          // MCTS.py:194
+                    kill_lowest_in_group(s.alive, ei.rs, ei.rlen);
+                    n_alive -= 2;
+                    steps += 1;
+                }
+            }
+        }
+        if (!__any_sync(FULLMASK, active)) break;
+    }
+    return steps;
+}
+
+}  // namespace bp
