@@ -82,7 +82,8 @@ struct SearchParams {
     // lane-per-rollout tables of the current state of each problem (lanes.cuh)
     int use_lanes;
     uint32_t* planes;        // [P][8][4] bit-sliced column heights
-    EntryInfo* einfo;        // [P][ES]
+    uint32_t* groups;        // [P][ES][8] equal-entry / rotated-entry masks
+    uint2* tile;             // [P][ES] (h | w << 8, (1 << w) - 1)
     uint32_t* wmask;         // [P][129][4] entries with w <= x
     uint32_t* hmask;         // [P][129][4] entries with h <= y
 };
@@ -161,8 +162,7 @@ fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
 // ------------------------------------------------------- lane-per-rollout kernel
 // Same tasks and the same 8-byte record as fs_rollout_kernel, but lane i plays rollout i of
 // the chunk on its own bit-sliced board (lanes.cuh): ~25x fewer warp instructions per
-// placement.  Used when every problem starts from an empty board (skyline invariant) and
-// equal tiles are adjacent in the tile list (always true for the reference's sorted lists).
+// placement.  Used when every problem starts from an empty board (skyline invariant).
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
 fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
@@ -170,7 +170,8 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     constexpr int WROWS = 32 * W + 1, HROWS = (1 << NB) + 1, NE = 32 * EW;
     __shared__ uint32_t s_wmask[4][WROWS * EW];
     __shared__ uint32_t s_hmask[4][HROWS * EW];
-    __shared__ EntryInfo s_einfo[4][NE];
+    __shared__ __align__(16) uint32_t s_groups[4][NE * 2 * EW];
+    __shared__ uint2 s_tile[4][NE];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const unsigned n_children = p.child_count[depth_slot * N_CLASSES + cls];
@@ -202,11 +203,15 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
                 const int y = i / EW, q = i % EW;
                 s_hmask[warp][i] = (y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
             }
-            const EntryInfo* ge = p.einfo + (size_t)prob * p.es;
-            for (int i = lane; i < NE; i += 32) {
-                EntryInfo z = {0, 0, 0, 0, 0, 0, 0, 0};
-                s_einfo[warp][i] = (i < d.n_entries) ? ge[i] : z;
+            const uint32_t* gg = p.groups + (size_t)prob * p.es * LANES_GROUP_WORDS;
+            for (int i = lane; i < NE * 2 * EW; i += 32) {
+                const int e = i / (2 * EW), q = i % (2 * EW);
+                s_groups[warp][i] = (e < d.n_entries)
+                    ? gg[e * LANES_GROUP_WORDS + (q < EW ? q : 4 + q - EW)] : 0u;
             }
+            const uint2* gt = p.tile + (size_t)prob * p.es;
+            for (int i = lane; i < NE; i += 32)
+                s_tile[warp][i] = (i < d.n_entries) ? gt[i] : make_uint2(0u, 0u);
             __syncwarp();
             cached_prob = prob;
         }
@@ -220,13 +225,13 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
             for (int q = 0; q < W; ++q) s.pl[b][q] = gp[b * 4 + q];
 #pragma unroll
         for (int q = 0; q < EW; ++q) s.alive[q] = word_range(0, lfb.w, q);
-        const EntryInfo ei = s_einfo[warp][entry];
+        const uint2 et = s_tile[warp][entry];
         uint32_t foot[W];
 #pragma unroll
-        for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + ei.w, q);
-        lanes_place(s, foot, lfb.x + ei.h);
-        kill_lowest_in_group(s.alive, ei.gs, ei.glen);
-        kill_lowest_in_group(s.alive, ei.rs, ei.rlen);
+        for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)(et.x >> 8), q);
+        lanes_place(s, foot, lfb.x, lfb.x + (int)(et.x & 0xFFu));
+        kill_lowest(s.alive, &s_groups[warp][entry * 2 * EW]);
+        kill_lowest(s.alive, &s_groups[warp][entry * 2 * EW + EW]);
         const int n_alive = lfb.w - 2;
         const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
 
@@ -234,7 +239,8 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
         const int count = min(CHUNK, p.n_local - first);
         bool my_solved;
         const int my_steps = lanes_rollout<NB, W, EW>(
-            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_einfo[warp], p.seed, d.stream, tag,
+            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_groups[warp], s_tile[warp], p.seed,
+            d.stream, tag,
             (uint32_t)(p.sim_begin + first + lane), lane < count, my_solved);
 
         const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved);
@@ -291,35 +297,35 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
         for (int q = 0; q < 4; ++q)
             if (lane == b * 4 + q) gp[lane] = (q < W) ? pl[b][q < W ? q : 0] : 0xFFFFFFFFu;
 
-    // ---- per-entry record: tile, its group of equal entries, its rotation's group -------
-    __syncwarp();
-#pragma unroll
-    for (int j = 0; j < EJ; ++j) sh_ent[lane + 32 * j] = (uint16_t)s.ent[j];
-    __syncwarp();
-    EntryInfo* ge = p.einfo + (size_t)prob * p.es;
+    // ---- per-entry tile record and the masks of equal / rotated live entries -------------
+    uint2* gt = p.tile + (size_t)prob * p.es;
 #pragma unroll
     for (int j = 0; j < EJ; ++j) {
         const int e = lane + 32 * j;
         if (e < d.n_entries) {
-            EntryInfo ei = {0, 0, 0, 0, 0, 0, 0, 0};
-            const uint16_t v = sh_ent[e];
-            if (e < n_alive && v != 0) {
-                const uint16_t rot = (uint16_t)((v >> 8) | (v << 8));
-                int gs = e, ge_ = e + 1;
-                while (gs > 0 && sh_ent[gs - 1] == v) --gs;
-                while (ge_ < n_alive && sh_ent[ge_] == v) ++ge_;
-                int rs = 0, re = 0;
-                for (int i = 0; i < n_alive; ++i)
-                    if (sh_ent[i] == rot) { rs = i; re = i + 1; break; }
-                while (re > 0 && re < n_alive && sh_ent[re] == rot) ++re;
-                ei.h = (uint8_t)(v & 0xFF); ei.w = (uint8_t)(v >> 8);
-                ei.gs = (uint8_t)gs; ei.glen = (uint8_t)(ge_ - gs);
-                ei.rs = (uint8_t)rs; ei.rlen = (uint8_t)(re - rs);
-            }
-            ge[e] = ei;
+            const uint32_t wdt = s.ent[j] >> 8;
+            gt[e] = make_uint2(s.ent[j], wdt >= 32u ? 0xFFFFFFFFu : ((1u << wdt) - 1u));
         }
     }
-    __syncwarp();
+    uint32_t* gg = p.groups + (size_t)prob * p.es * LANES_GROUP_WORDS;
+    for (int e = 0; e < n_alive; ++e) {
+        uint32_t mine = s.ent[0];
+#pragma unroll
+        for (int j = 1; j < EJ; ++j) mine = ((e >> 5) == j) ? s.ent[j] : mine;
+        const uint32_t v = __shfl_sync(FULLMASK, mine, e & 31);
+        const uint32_t rot = ((v & 0xFFu) << 8) | (v >> 8);
+        uint32_t m[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+#pragma unroll
+        for (int j = 0; j < EJ; ++j) {
+            m[j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == v);
+            m[4 + j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == rot);
+        }
+        uint32_t out = m[0];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) out = (lane == q) ? m[q] : out;
+        if (lane < 8) gg[e * LANES_GROUP_WORDS + lane] = out;
+    }
+    (void)sh_ent;
 
     // ---- wmask[x] = entries with w <= x, hmask[y] = entries with h <= y ------------------
     uint32_t* gw = p.wmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
@@ -774,22 +780,10 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
         }
     }
 
-    // lane-per-rollout kernel: needs the skyline invariant (empty initial boards) and equal
-    // tiles adjacent in every tile list; BP_ROLLOUT=warp forces the warp-per-board kernel
+    // lane-per-rollout kernel: needs the skyline invariant (empty initial boards);
+    // BP_ROLLOUT=warp forces the warp-per-board kernel
     bool lanes_ok = boards == nullptr;
     if (const char* env = getenv("BP_ROLLOUT")) lanes_ok = lanes_ok && strcmp(env, "warp") != 0;
-    for (int i = 0; i < n_problems && lanes_ok; ++i) {
-        const uint8_t* t = tiles + (size_t)i * entry_stride * 2;
-        std::vector<int> closed;
-        int prev = -1;
-        for (int e = 0; e < n_entries[i]; ++e) {
-            const int v = t[2 * e] | (t[2 * e + 1] << 8);
-            if (v == 0 || v == prev) continue;
-            if (std::find(closed.begin(), closed.end(), v) != closed.end()) { lanes_ok = false; break; }
-            if (prev >= 0) closed.push_back(prev);
-            prev = v;
-        }
-    }
     p.use_lanes = lanes_ok ? 1 : 0;
 
     int rc = BP_OK;
@@ -823,7 +817,8 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
     TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
     if (p.use_lanes) {
         TRY(dev_alloc(s, &p.planes, P * LANES_PLANE_STRIDE));
-        TRY(dev_alloc(s, &p.einfo, P * p.es));
+        TRY(dev_alloc(s, &p.groups, P * p.es * LANES_GROUP_WORDS));
+        TRY(dev_alloc(s, &p.tile, P * p.es));
         TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
         TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
     }

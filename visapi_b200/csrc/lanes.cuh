@@ -32,17 +32,16 @@
 
 namespace bp {
 
-// per-entry record prepared by the advance kernel (8 bytes)
-struct __align__(8) EntryInfo {
-    uint8_t h, w;          // tile (0, 0 = absent)
-    uint8_t gs, glen;      // group of entries equal to (h, w): [gs, gs + glen)
-    uint8_t rs, rlen;      // group of entries equal to (w, h)
-    uint8_t pad0, pad1;
-};
-
-constexpr int LANES_TABLE_ROWS = 129;   // wmask / hmask rows per problem in HBM (index 0..128)
-constexpr int LANES_MASK_WORDS = 4;     // words per table row in HBM (128 entries)
-constexpr int LANES_PLANE_STRIDE = 32;  // words per problem: planes[8][4]
+// Per-problem tables prepared once per depth by the advance kernel (write_lane_tables):
+//   planes[8][4]        bit-sliced column heights of the current board
+//   wmask[x][4], hmask[y][4]   live entries with w <= x / h <= y   (x, y = 0..128)
+//   groups[e][8]        words 0..3: live entries equal to entry e, words 4..7: live entries
+//                       equal to its rotation (any list order: groups need not be adjacent)
+//   tile[e]             (h | w << 8, low word of the width mask (1 << w) - 1)
+constexpr int LANES_TABLE_ROWS = 129;
+constexpr int LANES_MASK_WORDS = 4;
+constexpr int LANES_PLANE_STRIDE = 32;
+constexpr int LANES_GROUP_WORDS = 8;
 
 template <int NB, int W, int EW>
 struct LaneBoard {
@@ -69,14 +68,14 @@ __device__ __forceinline__ int select_bit32(uint32_t m, int k)
     return pos;
 }
 
-// clear the lowest set bit of (alive & group [gs, gs+glen)); returns false if the group is empty
+// clear the lowest set bit of (alive & group); returns false if there is none
 template <int EW>
-__device__ __forceinline__ bool kill_lowest_in_group(uint32_t (&alive)[EW], int gs, int glen)
+__device__ __forceinline__ bool kill_lowest(uint32_t (&alive)[EW], const uint32_t* group)
 {
     bool done = false;
 #pragma unroll
     for (int q = 0; q < EW; ++q) {
-        const uint32_t m = alive[q] & word_range(gs, gs + glen, q);
+        const uint32_t m = alive[q] & group[q];
         const uint32_t low = done ? 0u : (m & (0u - m));
         alive[q] ^= low;
         done = done || (m != 0u);
@@ -84,15 +83,18 @@ __device__ __forceinline__ bool kill_lowest_in_group(uint32_t (&alive)[EW], int 
     return done;
 }
 
-// set the heights of columns [c, c + w) to `height` (they all had the same height before)
+// raise the footprint columns from height `from` (all of them) to `to`: flip plane b under
+// the footprint wherever bit b differs
 template <int NB, int W, int EW>
-__device__ __forceinline__ void lanes_place(LaneBoard<NB, W, EW>& s, const uint32_t (&foot)[W], int height)
+__device__ __forceinline__ void lanes_place(LaneBoard<NB, W, EW>& s, const uint32_t (&foot)[W], int from, int to)
 {
+    const int diff = from ^ to;
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        const uint32_t on = ((height >> b) & 1) ? 0xFFFFFFFFu : 0u;
+        if ((diff >> b) & 1) {
 #pragma unroll
-        for (int q = 0; q < W; ++q) s.pl[b][q] = (s.pl[b][q] & ~foot[q]) | (foot[q] & on);
+            for (int q = 0; q < W; ++q) s.pl[b][q] ^= foot[q];
+        }
     }
 }
 
@@ -119,13 +121,14 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
 
 // One rollout per lane, all 32 lanes of the warp in lock step (same child, sims sim0 + lane).
 // `root` is the child state (identical in every lane).  Tables live in this warp's shared
-// memory: wmask[(x) * EW + q], hmask[(y) * EW + q], einfo[e].
+// memory: wmask[x * EW + q], hmask[y * EW + q], groups[e * 2 * EW + ..], tile[e].
 // Returns the number of placements of this lane's rollout; solved = all tiles used.
 template <int NB, int W, int EW>
 __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, int n_alive,
                                              const uint32_t* __restrict__ wmask,
                                              const uint32_t* __restrict__ hmask,
-                                             const EntryInfo* __restrict__ einfo, uint32_t seed,
+                                             const uint32_t* __restrict__ groups,
+                                             const uint2* __restrict__ tile, uint32_t seed,
                                              uint32_t stream, uint32_t tag, uint32_t sim, bool active,
                                              bool& solved)
 {
@@ -145,12 +148,12 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                 bool go = hmin < rows;                       // else: full board, tiles left
                 // first candidate column and the run of candidates that starts there
                 uint32_t foot[W];
+                uint32_t colbit1 = 0u;
                 int col = 0, run = 0;
                 if (W == 1) {
-                    const uint32_t colbit = cand[0] & (0u - cand[0]);
-                    const uint32_t runmask = cand[0] & ~(cand[0] + colbit);
+                    colbit1 = cand[0] & (0u - cand[0]);
+                    const uint32_t runmask = cand[0] & ~(cand[0] + colbit1);
                     run = __popc(runmask);
-                    col = __popc(colbit - 1u);
                 } else if (W == 2) {
                     const unsigned long long c64 =
                         (unsigned long long)cand[0] | ((unsigned long long)cand[W > 1 ? 1 : 0] << 32);
@@ -191,8 +194,9 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                 if (!go) {
                     active = false;
                 } else {
-                    const int w4 = it & 3;
-                    const uint32_t u = w4 == 0 ? rnd.x : (w4 == 1 ? rnd.y : (w4 == 2 ? rnd.z : rnd.w));
+                    const uint32_t lo = (it & 1) ? rnd.y : rnd.x;
+                    const uint32_t hi = (it & 1) ? rnd.w : rnd.z;
+                    const uint32_t u = (it & 2) ? hi : lo;
                     int idx = (int)__umulhi(u, (uint32_t)k);                // MCTS.py:174
                     uint32_t m = legal[0];
                     int base = 0;
@@ -205,13 +209,17 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         base = past ? 32 * q : base;
                     }
                     const int e = base + select_bit32(m, idx);
-                    const EntryInfo ei = einfo[e];
-                    // footprint columns [col, col + w)
+                    const uint2 t = tile[e];                                // (h | w << 8, (1 << w) - 1)
+                    const int th = (int)(t.x & 0xFFu), tw = (int)(t.x >> 8);
+                    if (W == 1) {
+                        foot[0] = colbit1 * t.y;                            // width mask shifted to col
+                    } else {
 #pragma unroll
-                    for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + ei.w, q);
-                    lanes_place(s, foot, hmin + ei.h);                      // MCTS.py:175-178
-                    kill_lowest_in_group(s.alive, ei.gs, ei.glen);          // MCTS.py:194
-                    kill_lowest_in_group(s.alive, ei.rs, ei.rlen);
+                        for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
+                    }
+                    lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
+                    kill_lowest(s.alive, groups + e * 2 * EW);              // MCTS.py:194
+                    kill_lowest(s.alive, groups + e * 2 * EW + EW);
                     n_alive -= 2;
                     steps += 1;
                 }
