@@ -290,6 +290,7 @@ int bp_destroy(bp_context* ctx)
     if (!ctx) return BP_OK;
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
+    if (ctx->arena) cudaFree(ctx->arena);
     delete ctx;
     return BP_OK;
 }

@@ -19,6 +19,10 @@ struct bp_context {
     // grow-only device scratch for the batched calls
     void* scratch = nullptr;
     size_t scratch_bytes = 0;
+    // grow-only arena lent to one one-shot bp_flat_search at a time
+    void* arena = nullptr;
+    size_t arena_bytes = 0;
+    bool arena_busy = false;
 };
 
 namespace bp {

@@ -28,6 +28,8 @@ constexpr int CHUNK = 32;              // rollouts per task = one result per lan
 constexpr int ADV_WARPS = 4;
 constexpr uint32_t NONE_U32 = 0xFFFFFFFFu;
 constexpr int MAX_DEPTHS = BP_MAX_ENTRIES / 2 + 1;
+// search class = (height planes the rows need: 5..8) x (warp shape class RHO, W, EJ)
+constexpr int FS_CLASSES = 4 * N_CLASSES;
 
 enum Status : int { ST_ACTIVE = 0, ST_SOLVED = 1, ST_DEAD = 2 };
 
@@ -77,11 +79,11 @@ struct SearchParams {
     ChunkRec* rec;           // [P][ES][NC]
     ChildStats* stats;       // [P][ES]
     uint32_t* child_list;    // per class segments
-    unsigned* child_count;   // [MAX_DEPTHS + 1][N_CLASSES]
-    unsigned* task_counter;  // [MAX_DEPTHS + 1][N_CLASSES]
+    unsigned* child_count;   // [MAX_DEPTHS + 1][FS_CLASSES]
+    unsigned* task_counter;  // [MAX_DEPTHS + 1][FS_CLASSES]
     // lane-per-rollout tables of the current state of each problem (lanes.cuh)
     int use_lanes;
-    uint32_t* planes;        // [P][8][4] bit-sliced column heights
+    uint32_t* planes;        // [P][8][4] bit-sliced column heights, inverted
     uint32_t* groups;        // [P][ES][8] equal-entry / rotated-entry masks
     uint2* tile;             // [P][ES] (h | w << 8, (1 << w) - 1)
     uint32_t* wmask;         // [P][129][4] entries with w <= x
@@ -103,9 +105,9 @@ __global__ void __launch_bounds__(128)
 fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
 {
     const int lane = lane_id();
-    const unsigned n_children = p.child_count[depth_slot * N_CLASSES + cls];
+    const unsigned n_children = p.child_count[depth_slot * FS_CLASSES + cls];
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
-    unsigned* counter = &p.task_counter[depth_slot * N_CLASSES + cls];
+    unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
     for (;;) {
         unsigned long long task = 0;
         if (lane == 0) task = atomicAdd(counter, 1u);
@@ -174,9 +176,9 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     __shared__ uint2 s_tile[4][NE];
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    const unsigned n_children = p.child_count[depth_slot * N_CLASSES + cls];
+    const unsigned n_children = p.child_count[depth_slot * FS_CLASSES + cls];
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
-    unsigned* counter = &p.task_counter[depth_slot * N_CLASSES + cls];
+    unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
     int cached_prob = -1;
     for (;;) {
         unsigned long long task = 0;
@@ -237,13 +239,13 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
 
         const int first = chunk * CHUNK;
         const int count = min(CHUNK, p.n_local - first);
-        bool my_solved;
+        int my_solved;
         const int my_steps = lanes_rollout<NB, W, EW>(
             s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_groups[warp], s_tile[warp], p.seed,
             d.stream, tag,
-            (uint32_t)(p.sim_begin + first + lane), lane < count, my_solved);
+            (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
 
-        const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved);
+        const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved != 0);
         const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
         const int mx = __reduce_max_sync(FULLMASK, my_steps);
         const int sum = __reduce_add_sync(FULLMASK, my_steps);
@@ -295,7 +297,7 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
     for (int b = 0; b < 8; ++b)
 #pragma unroll
         for (int q = 0; q < 4; ++q)
-            if (lane == b * 4 + q) gp[lane] = (q < W) ? pl[b][q < W ? q : 0] : 0xFFFFFFFFu;
+            if (lane == b * 4 + q) gp[lane] = (q < W) ? ~pl[b][q < W ? q : 0] : 0u;   // inverted
 
     // ---- per-entry tile record and the masks of equal / rotated live entries -------------
     uint2* gt = p.tile + (size_t)prob * p.es;
@@ -606,7 +608,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
         if (status != ST_SOLVED && n_alive > 0 && r >= 0)
             p.n_tiles_placed[prob] += (unsigned long long)n_alive;   // one attempt per entry (:60)
         if (k > 0) {
-            base = atomicAdd(&p.child_count[next_slot * N_CLASSES + cls], (unsigned)k);
+            base = atomicAdd(&p.child_count[next_slot * FS_CLASSES + cls], (unsigned)k);
             p.rollouts_executed[prob] += (unsigned long long)k * p.n_local;
         }
     }
@@ -628,12 +630,13 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
 // ================================================================= host side
 using namespace bp;
 
-// lane-kernel instantiation for a warp shape class: NB height planes cover the rows of the
-// class (RHO = 1: <= 32 rows -> 6 planes, 2: <= 64 -> 7, 4: <= 128 -> 8)
+// lane-kernel instantiation of a search class: NB height planes, W words per plane, EW words
+// of entry mask
 template <typename F>
-static void dispatch_lanes(int cls, F&& f)
+static void dispatch_lanes(int scls, F&& f)
 {
-    const int ej = cls % 3, w = (cls / 3) % 3, rho = cls / 9;
+    const int cls = scls % N_CLASSES, nb = 5 + scls / N_CLASSES;
+    const int ej = cls % 3, w = (cls / 3) % 3;
     auto with_ew = [&](auto NBc, auto Wc) {
         if (ej <= 1) f(NBc, Wc, IC<2>{}); else f(NBc, Wc, IC<4>{});
     };
@@ -644,9 +647,10 @@ static void dispatch_lanes(int cls, F&& f)
             default: with_ew(NBc, IC<4>{}); break;
         }
     };
-    switch (rho) {
-        case 0: with_w(IC<6>{}); break;
-        case 1: with_w(IC<7>{}); break;
+    switch (nb) {
+        case 5: with_w(IC<5>{}); break;
+        case 6: with_w(IC<6>{}); break;
+        case 7: with_w(IC<7>{}); break;
         default: with_w(IC<8>{}); break;
     }
 }
@@ -663,45 +667,49 @@ struct bp_search {
     std::vector<uint32_t> h_boards;
     // class bookkeeping
     std::vector<int> classes;                   // classes present
-    int cls_count[N_CLASSES] = {0};
-    int cls_prob_off[N_CLASSES] = {0};          // offset into d_cls_problems
-    int cls_list_off[N_CLASSES] = {0};          // offset into child_list
-    int grid_rollout[N_CLASSES] = {0};
-    int grid_lanes[N_CLASSES] = {0};
+    int cls_count[FS_CLASSES] = {0};
+    int cls_prob_off[FS_CLASSES] = {0};          // offset into d_cls_problems
+    int cls_list_off[FS_CLASSES] = {0};          // offset into child_list
+    int grid_rollout[FS_CLASSES] = {0};
+    int grid_lanes[FS_CLASSES] = {0};
     int* d_cls_problems = nullptr;
     ProblemDesc* d_desc = nullptr;
     uint32_t* d_init_occ = nullptr;            // initial boards (NULL: empty boards)
     uint8_t* d_init_tiles = nullptr;           // initial tile tables
-    std::vector<void*> allocs;
+    char* arena = nullptr;
+    size_t arena_used = 0, arena_bytes = 0;
+    bool arena_from_ctx = false;
     size_t counters_bytes = 0;
     // optional per-depth CUDA-event timing of the rollout and advance launches
     bool profiling = false;
     std::vector<cudaEvent_t> ev;               // 3 per depth: before rollouts, between, after advance
     int ev_depths = 0;
-    ~bp_search() { for (cudaEvent_t e : ev) cudaEventDestroy(e); }
+    // one stream per search class: classes hold disjoint problems, so their depth loops run
+    // concurrently and one class's advance (latency-bound) hides under another's rollouts
+    std::vector<cudaStream_t> cls_stream;
+    std::vector<cudaEvent_t> cls_done;
+    std::vector<int> cls_depth;
+    cudaEvent_t fork_ev = nullptr;
+    ~bp_search()
+    {
+        for (cudaEvent_t e : ev) cudaEventDestroy(e);
+        for (cudaStream_t st : cls_stream) cudaStreamDestroy(st);
+        for (cudaEvent_t e : cls_done) cudaEventDestroy(e);
+        if (fork_ev) cudaEventDestroy(fork_ev);
+    }
 };
 
+// All device arrays of a search live in one arena: a single cudaMalloc (or, for the one-shot
+// bp_flat_search, a grow-only arena cached in the context, so repeated calls allocate nothing).
+// dev_alloc is called twice over the same sequence: a dry run that only sizes the arena, then
+// the run that hands out the slices.
 template <typename T>
 static int dev_alloc(bp_search* s, T** out, size_t count)
 {
-    void* ptr = nullptr;
-    BP_CUDA(cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T)));
-    s->allocs.push_back(ptr);
-    *out = static_cast<T*>(ptr);
+    const size_t bytes = (std::max<size_t>(count, 1) * sizeof(T) + 255) & ~size_t(255);
+    *out = s->arena ? reinterpret_cast<T*>(s->arena + s->arena_used) : nullptr;
+    s->arena_used += bytes;
     return BP_OK;
-}
-
-static int alloc_records(bp_search* s)
-{
-    // (re)allocate the chunk records for the current partition
-    SearchParams& p = s->p;
-    if (p.rec) {
-        auto it = std::find(s->allocs.begin(), s->allocs.end(), (void*)p.rec);
-        if (it != s->allocs.end()) s->allocs.erase(it);
-        BP_CUDA(cudaFree(p.rec));
-        p.rec = nullptr;
-    }
-    return dev_alloc(s, &p.rec, (size_t)p.n_problems * p.es * p.n_chunks);
 }
 
 extern "C" {
@@ -711,15 +719,18 @@ int bp_search_destroy(bp_search* s)
     if (!s) return BP_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
-    for (void* ptr : s->allocs) cudaFree(ptr);
+    if (s->arena_from_ctx) s->ctx->arena_busy = false;
+    else if (s->arena) cudaFree(s->arena);
     delete s;
     return BP_OK;
 }
 
-int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const int32_t* cols,
-                     const int32_t* n_entries, const uint8_t* tiles, int entry_stride,
-                     const uint32_t* boards, const uint32_t* streams, int n_sim, int strategy,
-                     uint32_t seed, bp_search** out)
+}  // extern "C"
+
+static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, const int32_t* cols,
+                         const int32_t* n_entries, const uint8_t* tiles, int entry_stride,
+                         const uint32_t* boards, const uint32_t* streams, int n_sim, int strategy,
+                         uint32_t seed, bool use_ctx_arena, bp_search** out)
 {
     BP_REQUIRE(ctx && out && rows && cols && n_entries && tiles, "null argument");
     BP_REQUIRE(n_problems >= 1 && n_problems < (1 << 24), "n_problems must be 1..2^24-1");
@@ -755,11 +766,12 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
     s->max_depth = max_n;
 
     s->h_desc.resize(n_problems);
-    std::vector<std::vector<int>> by_class(N_CLASSES);
+    std::vector<std::vector<int>> by_class(FS_CLASSES);
     for (int i = 0; i < n_problems; ++i) {
         ProblemDesc& d = s->h_desc[i];
         d.rows = rows[i]; d.cols = cols[i]; d.n_entries = n_entries[i];
-        d.cls = shape_class(rows[i], cols[i], n_entries[i]);
+        const int nb = rows[i] <= 31 ? 5 : (rows[i] <= 63 ? 6 : (rows[i] <= 127 ? 7 : 8));
+        d.cls = (nb - 5) * N_CLASSES + shape_class(rows[i], cols[i], n_entries[i]);
         d.stream = streams ? streams[i] : (uint32_t)i;
         d.pad0 = d.pad1 = d.pad2 = 0;
         by_class[d.cls].push_back(i);
@@ -769,7 +781,7 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
 
     std::vector<int> cls_problems;
     int list_off = 0;
-    for (int c = 0; c < N_CLASSES; ++c) {
+    for (int c = 0; c < FS_CLASSES; ++c) {
         s->cls_count[c] = (int)by_class[c].size();
         s->cls_prob_off[c] = (int)cls_problems.size();
         s->cls_list_off[c] = list_off;
@@ -787,42 +799,80 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
     p.use_lanes = lanes_ok ? 1 : 0;
 
     int rc = BP_OK;
-#define TRY(x) do { rc = (x); if (rc) { bp_search_destroy(s); return rc; } } while (0)
+#define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
     const size_t P = n_problems;
-    TRY(dev_alloc(s, &s->d_desc, P));
-    p.desc = s->d_desc;
-    TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));
-    TRY(dev_alloc(s, &p.tiles, P * p.es * 2));
-    TRY(dev_alloc(s, &p.lfb, P));
-    TRY(dev_alloc(s, &p.legal, P));
-    TRY(dev_alloc(s, &p.status, P));
-    TRY(dev_alloc(s, &p.depth, P));
-    TRY(dev_alloc(s, &p.n_tiles_placed, P));
-    TRY(dev_alloc(s, &p.rollouts, P));
-    TRY(dev_alloc(s, &p.rollout_placements, P));
-    TRY(dev_alloc(s, &p.rollouts_executed, P));
-    TRY(dev_alloc(s, &p.placements_executed, P));
-    TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
-    if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
-    TRY(dev_alloc(s, &p.prev_tile, P));
-    TRY(dev_alloc(s, &p.n_order, P));
-    TRY(dev_alloc(s, &p.order, P * (p.es / 2 + 2) * 2));
-    TRY(dev_alloc(s, &p.path, P * (p.es / 2)));
-    TRY(dev_alloc(s, &p.child_scores, P * (p.es / 2) * p.es));
-    TRY(dev_alloc(s, &p.stats, P * p.es));
-    TRY(dev_alloc(s, &p.child_list, (size_t)std::max(list_off, 1)));
-    s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * N_CLASSES * sizeof(unsigned);
-    TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * N_CLASSES));
-    TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * N_CLASSES));
-    TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
-    if (p.use_lanes) {
-        TRY(dev_alloc(s, &p.planes, P * LANES_PLANE_STRIDE));
-        TRY(dev_alloc(s, &p.groups, P * p.es * LANES_GROUP_WORDS));
-        TRY(dev_alloc(s, &p.tile, P * p.es));
-        TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
-        TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+    auto carve = [&]() -> int {
+        s->arena_used = 0;
+        TRY(dev_alloc(s, &s->d_desc, P));
+        p.desc = s->d_desc;
+        TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));
+        TRY(dev_alloc(s, &p.tiles, P * p.es * 2));
+        TRY(dev_alloc(s, &p.lfb, P));
+        TRY(dev_alloc(s, &p.legal, P));
+        TRY(dev_alloc(s, &p.status, P));
+        TRY(dev_alloc(s, &p.depth, P));
+        TRY(dev_alloc(s, &p.n_tiles_placed, P));
+        TRY(dev_alloc(s, &p.rollouts, P));
+        TRY(dev_alloc(s, &p.rollout_placements, P));
+        TRY(dev_alloc(s, &p.rollouts_executed, P));
+        TRY(dev_alloc(s, &p.placements_executed, P));
+        TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
+        if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
+        TRY(dev_alloc(s, &p.prev_tile, P));
+        TRY(dev_alloc(s, &p.n_order, P));
+        TRY(dev_alloc(s, &p.order, P * (p.es / 2 + 2) * 2));
+        TRY(dev_alloc(s, &p.path, P * (p.es / 2)));
+        TRY(dev_alloc(s, &p.child_scores, P * (p.es / 2) * p.es));
+        TRY(dev_alloc(s, &p.stats, P * p.es));
+        TRY(dev_alloc(s, &p.child_list, (size_t)std::max(list_off, 1)));
+        s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * FS_CLASSES * sizeof(unsigned);
+        TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * FS_CLASSES));
+        TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * FS_CLASSES));
+        TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
+        if (p.use_lanes) {
+            TRY(dev_alloc(s, &p.planes, P * LANES_PLANE_STRIDE));
+            TRY(dev_alloc(s, &p.groups, P * p.es * LANES_GROUP_WORDS));
+            TRY(dev_alloc(s, &p.tile, P * p.es));
+            TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+            TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+        }
+        TRY(dev_alloc(s, &p.rec, P * p.es * (size_t)p.n_chunks));
+        return BP_OK;
+    };
+    rc = carve();                                   // dry run: size
+    if (rc) { bp_search_destroy(s); return rc; }
+    const size_t need = s->arena_used;
+    if (use_ctx_arena && !ctx->arena_busy) {
+        if (ctx->arena_bytes < need) {
+            if (ctx->arena) {
+                cudaStreamSynchronize(ctx->stream);
+                cudaFree(ctx->arena);
+                ctx->arena = nullptr;
+                ctx->arena_bytes = 0;
+            }
+            const size_t want = need + need / 4;
+            if (cudaMalloc(&ctx->arena, want) != cudaSuccess) {
+                set_error("cudaMalloc of %zu bytes failed", want);
+                bp_search_destroy(s);
+                return BP_ERR_CUDA;
+            }
+            ctx->arena_bytes = want;
+        }
+        s->arena = static_cast<char*>(ctx->arena);
+        s->arena_from_ctx = true;
+        ctx->arena_busy = true;
+    } else {
+        void* ptr = nullptr;
+        if (cudaMalloc(&ptr, need) != cudaSuccess) {
+            set_error("cudaMalloc of %zu bytes failed", need);
+            bp_search_destroy(s);
+            return BP_ERR_CUDA;
+        }
+        s->arena = static_cast<char*>(ptr);
     }
-    TRY(alloc_records(s));
+    s->arena_bytes = need;
+    rc = carve();                                   // hand out the slices
+    if (rc) { bp_search_destroy(s); return rc; }
 #undef TRY
     BP_CUDA(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc),
                             cudaMemcpyHostToDevice, ctx->stream));
@@ -838,7 +888,7 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
     // persistent grid per class: every SM filled to the occupancy limit of that kernel
     for (int c : s->classes) {
         int per_sm = 1;
-        dispatch_class(c, [&](auto R, auto Wc, auto E) {
+        dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
             cudaOccupancyMaxActiveBlocksPerMultiprocessor(
                 &per_sm, fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>,
                 128, 0);
@@ -855,8 +905,32 @@ int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const
             s->grid_lanes[c] = ctx->sm_count * std::max(per_sm_l, 1);
         }
     }
+    BP_CUDA(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
+    for (int c : s->classes) {
+        cudaStream_t st;
+        cudaEvent_t e;
+        BP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        BP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->cls_stream.push_back(st);
+        s->cls_done.push_back(e);
+        int md = 0;
+        for (int i = 0; i < n_problems; ++i)
+            if (s->h_desc[i].cls == c) md = std::max(md, s->h_desc[i].n_entries / 2);
+        s->cls_depth.push_back(md);
+    }
     *out = s;
     return BP_OK;
+}
+
+extern "C" {
+
+int bp_search_create(bp_context* ctx, int n_problems, const int32_t* rows, const int32_t* cols,
+                     const int32_t* n_entries, const uint8_t* tiles, int entry_stride,
+                     const uint32_t* boards, const uint32_t* streams, int n_sim, int strategy,
+                     uint32_t seed, bp_search** out)
+{
+    return search_create(ctx, n_problems, rows, cols, n_entries, tiles, entry_stride, boards,
+                         streams, n_sim, strategy, seed, false, out);
 }
 
 int bp_search_set_partition(bp_search* s, int rank, int n_ranks, int sim_begin, int n_local)
@@ -872,25 +946,45 @@ int bp_search_set_partition(bp_search* s, int rank, int n_ranks, int sim_begin, 
     s->p.n_local = n_local;
     s->p.n_chunks = std::max(1, (n_local + CHUNK - 1) / CHUNK);
     s->ready = false;
-    return alloc_records(s);
+    return BP_OK;    // the record buffer was sized for all n_sim rollouts
 }
 
 }  // extern "C"
 
 template <bool FIRST>
+static void launch_advance_class(bp_search* s, int c, int next_slot, const ChildStats* gathered,
+                                 cudaStream_t st)
+{
+    const int n = s->cls_count[c];
+    const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
+    dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
+        fs_advance_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value, FIRST>
+            <<<grid, ADV_WARPS * 32, 0, st>>>(s->p, c, s->cls_list_off[c],
+                                              s->d_cls_problems + s->cls_prob_off[c], n, next_slot,
+                                              gathered);
+    });
+    s->ctx->launches++;
+}
+
+template <bool FIRST>
 static void launch_advance(bp_search* s, int next_slot, const ChildStats* gathered)
 {
-    for (int c : s->classes) {
-        const int n = s->cls_count[c];
-        const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
-        dispatch_class(c, [&](auto R, auto Wc, auto E) {
-            fs_advance_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value, FIRST>
-                <<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(
-                    s->p, c, s->cls_list_off[c], s->d_cls_problems + s->cls_prob_off[c], n,
-                    next_slot, gathered);
+    for (int c : s->classes) launch_advance_class<FIRST>(s, c, next_slot, gathered, s->ctx->stream);
+}
+
+static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t st)
+{
+    if (s->p.use_lanes)
+        dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
+            fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>
+                <<<s->grid_lanes[c], 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth);
         });
-        s->ctx->launches++;
-    }
+    else
+        dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
+            fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
+                <<<s->grid_rollout[c], 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth);
+        });
+    s->ctx->launches++;
 }
 
 extern "C" {
@@ -971,21 +1065,7 @@ int bp_search_step_rollouts(bp_search* s)
     }
     BP_CUDA(cudaSetDevice(s->ctx->device));
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth], s->ctx->stream));
-    for (int c : s->classes) {
-        if (s->p.use_lanes)
-            dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
-                fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>
-                    <<<s->grid_lanes[c], 128, 0, s->ctx->stream>>>(s->p, c, s->cls_list_off[c],
-                                                                   s->cur_depth);
-            });
-        else
-            dispatch_class(c, [&](auto R, auto Wc, auto E) {
-                fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
-                    <<<s->grid_rollout[c], 128, 0, s->ctx->stream>>>(s->p, c, s->cls_list_off[c],
-                                                                     s->cur_depth);
-            });
-        s->ctx->launches++;
-    }
+    for (int c : s->classes) launch_rollouts_class(s, c, s->cur_depth, s->ctx->stream);
     BP_CUDA(cudaGetLastError());
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth + 1], s->ctx->stream));
     return BP_OK;
@@ -998,7 +1078,7 @@ int bp_search_step_reduce(bp_search* s)
     for (int c : s->classes) {
         const int n = s->cls_count[c];
         const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
-        const int ej = c % 3 == 0 ? 1 : (c % 3 == 1 ? 2 : 4);
+        const int ej = (c % N_CLASSES) % 3 == 0 ? 1 : ((c % N_CLASSES) % 3 == 1 ? 2 : 4);
         const int* list = s->d_cls_problems + s->cls_prob_off[c];
         if (ej == 1) fs_reduce_kernel<1><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
         else if (ej == 2) fs_reduce_kernel<2><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
@@ -1051,12 +1131,35 @@ int bp_search_run(bp_search* s)
         set_error("bp_search_run is single-rank; use the step API with a partition");
         return BP_ERR_STATE;
     }
-    while (s->cur_depth < s->max_depth) {
-        int rc = bp_search_step_rollouts(s);
-        if (rc) return rc;
-        rc = bp_search_step_commit(s, nullptr);
-        if (rc) return rc;
+    if (s->profiling || s->classes.size() == 1 || getenv("BP_SERIAL_CLASSES")) {
+        while (s->cur_depth < s->max_depth) {
+            int rc = bp_search_step_rollouts(s);
+            if (rc) return rc;
+            rc = bp_search_step_commit(s, nullptr);
+            if (rc) return rc;
+        }
+        return BP_OK;
     }
+    if (!s->ready || s->cur_depth != 0) {
+        set_error("bp_search_run: call bp_search_reset first");
+        return BP_ERR_STATE;
+    }
+    // fork: every class runs its whole depth loop on its own stream, then join
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
+    for (size_t k = 0; k < s->classes.size(); ++k) {
+        const int c = s->classes[k];
+        cudaStream_t st = s->cls_stream[k];
+        BP_CUDA(cudaStreamWaitEvent(st, s->fork_ev, 0));
+        for (int d = 0; d < s->cls_depth[k]; ++d) {
+            launch_rollouts_class(s, c, d, st);
+            launch_advance_class<false>(s, c, d + 1, nullptr, st);
+        }
+        BP_CUDA(cudaGetLastError());
+        BP_CUDA(cudaEventRecord(s->cls_done[k], st));
+        BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->cls_done[k], 0));
+    }
+    s->cur_depth = s->max_depth;
     return BP_OK;
 }
 
@@ -1109,8 +1212,8 @@ int bp_flat_search(bp_context* ctx, int n_problems, const int32_t* rows, const i
                    int32_t* child_scores)
 {
     bp_search* s = nullptr;
-    int rc = bp_search_create(ctx, n_problems, rows, cols, n_entries, tiles, entry_stride, boards,
-                              streams, n_sim, strategy, seed, &s);
+    int rc = search_create(ctx, n_problems, rows, cols, n_entries, tiles, entry_stride, boards,
+                           streams, n_sim, strategy, seed, true, &s);
     if (rc) return rc;
     rc = bp_search_reset(s);
     if (!rc) rc = bp_search_run(s);

@@ -45,7 +45,7 @@ constexpr int LANES_GROUP_WORDS = 8;
 
 template <int NB, int W, int EW>
 struct LaneBoard {
-    uint32_t pl[NB][W];    // bit-sliced column heights
+    uint32_t pl[NB][W];    // bit-sliced column heights, stored INVERTED (bit set = height bit clear)
     uint32_t alive[EW];    // live entries of the (compacted) tile list
 };
 
@@ -84,16 +84,21 @@ __device__ __forceinline__ bool kill_lowest(uint32_t (&alive)[EW], const uint32_
 }
 
 // raise the footprint columns from height `from` (all of them) to `to`: flip plane b under
-// the footprint wherever bit b differs
+// the footprint wherever bit b differs (a flip is the same on inverted planes)
 template <int NB, int W, int EW>
 __device__ __forceinline__ void lanes_place(LaneBoard<NB, W, EW>& s, const uint32_t (&foot)[W], int from, int to)
 {
-    const int diff = from ^ to;
+    const uint32_t diff = (uint32_t)(from ^ to);
 #pragma unroll
     for (int b = 0; b < NB; ++b) {
-        if ((diff >> b) & 1) {
 #pragma unroll
-            for (int q = 0; q < W; ++q) s.pl[b][q] ^= foot[q];
+        for (int q = 0; q < W; ++q) {
+            // one test + one predicated XOR per plane word
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                "and.b32 t, %2, %3;\n\t"
+                "setp.ne.u32 p, t, 0;\n\t"
+                "@p xor.b32 %0, %0, %1;\n\t}"
+                : "+r"(s.pl[b][q]) : "r"(foot[q]), "r"(diff), "r"(1u << b));
         }
     }
 }
@@ -110,7 +115,7 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
         uint32_t z[W];
         uint32_t any = 0u;
 #pragma unroll
-        for (int q = 0; q < W; ++q) { z[q] = cand[q] & ~s.pl[b][q]; any |= z[q]; }
+        for (int q = 0; q < W; ++q) { z[q] = cand[q] & s.pl[b][q]; any |= z[q]; }
         const bool has_zero = any != 0u;          // some candidate has bit b of its height clear
 #pragma unroll
         for (int q = 0; q < W; ++q) cand[q] = has_zero ? z[q] : cand[q];
@@ -129,19 +134,19 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                                              const uint32_t* __restrict__ hmask,
                                              const uint32_t* __restrict__ groups,
                                              const uint2* __restrict__ tile, uint32_t seed,
-                                             uint32_t stream, uint32_t tag, uint32_t sim, bool active,
-                                             bool& solved)
+                                             uint32_t stream, uint32_t tag, uint32_t sim, int active,
+                                             int& solved)
 {
     int steps = 0;
-    solved = false;
+    solved = 0;
     Philox4 rnd = {0u, 0u, 0u, 0u};
     for (int it = 0;; ++it) {
         if ((it & 3) == 0)                                   // same iteration in every lane
             rnd = rollout_stream_block(seed, stream, tag, sim, (uint32_t)(it >> 2));
         if (active) {
             if (n_alive == 0) {                              // MCTS.py:167-169
-                solved = true;
-                active = false;
+                solved = 1;
+                active = 0;
             } else {
                 uint32_t cand[W];
                 const int hmin = lanes_min(s, cand);
@@ -192,7 +197,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                 }
                 go = go && (k != 0);                         // MCTS.py:171-172
                 if (!go) {
-                    active = false;
+                    active = 0;
                 } else {
                     const uint32_t lo = (it & 1) ? rnd.y : rnd.x;
                     const uint32_t hi = (it & 1) ? rnd.w : rnd.z;
@@ -225,7 +230,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                 }
             }
         }
-        if (!__any_sync(FULLMASK, active)) break;
+        if (!__any_sync(FULLMASK, active != 0)) break;
     }
     return steps;
 }
