@@ -46,8 +46,31 @@ def model_inst_per_placement(key):
     return float((4 + 2 * rho * w) + 4 * w + 6 * ej + 27 + 6 * ej + 6 * rho * w + 6 + 6)
 
 
-# raw ncu smsp__inst_executed.sum / placements of the round-1 v1 kernel (profiles/r1/)
+# raw ncu smsp__inst_executed.sum / placements of the warp-per-board kernel (profiles/r1/)
 MEASURED_INST_PER_PLACEMENT_V1 = {"1,1,2": 137.2, "1,2,2": 167.4, "2,1,2": 148.9, "2,2,2": 182.1}
+
+
+def model_lane_inst_per_placement(key):
+    """ALGORITHMIC thread instructions per placement of the lane-per-rollout kernel for lane
+    class "NB,W,EW" (NB height planes, W words per plane, EW words of entry mask); frozen in
+    DESIGN.md section 5 when the kernel was first measured: minimum search NB*(2W+2), column
+    and run 5W+2, legal mask 4+3EW, draw 15 (Philox4x32-10 amortised over 4 draws + index),
+    k-th-set select 5(EW-1)+32, table loads 4, place W+2*NB*W, pair removal 2(3EW+2), loop 8.
+    One warp instruction advances 32 lanes, so the warp-instruction equivalent is this / 32."""
+    nb, w, ew = (int(v) for v in key.split(","))
+    return float(nb * (2 * w + 2) + (5 * w + 2) + (4 + 3 * ew) + 15 + (5 * (ew - 1) + 32) + 4 +
+                 (w + 2 * nb * w) + 2 * (3 * ew + 2) + 8)
+
+
+# raw ncu thread instructions / placement and DRAM bytes / launch of that kernel (profiles/r1/)
+MEASURED_LANE_THREAD_INST = {"5,1,2": 196.4, "5,2,2": 255.7, "6,1,2": 205.9, "6,2,2": 267.5}
+MEASURED_LANE_DRAM_BYTES_PER_LAUNCH = 216647.0
+
+
+def lane_class_key(rows, cols, n_entries):
+    nb = 5 if rows <= 31 else (6 if rows <= 63 else (7 if rows <= 127 else 8))
+    w = 1 if cols <= 32 else (2 if cols <= 64 else 4)
+    return "%d,%d,%d" % (nb, w, 2 if n_entries <= 64 else 4)
 
 
 def parse_args():
@@ -281,13 +304,19 @@ def our_arm(a):
     rollout_ms, advance_ms, n_depths = search.profile()
     res_p = search.results()
     search.set_profiling(False)
-    keys = [shape_class_key(p.rows, p.cols, 2 * len(p.tiles)) for p in problems]
+    lane_kernel = search.info()["lane_kernel"]
+    if lane_kernel:
+        keys = [lane_class_key(p.rows, p.cols, 2 * len(p.tiles)) for p in problems]
+        per_placement = lambda k: model_lane_inst_per_placement(k) / 32.0   # noqa: E731
+    else:
+        keys = [shape_class_key(p.rows, p.cols, 2 * len(p.tiles)) for p in problems]
+        per_placement = model_inst_per_placement
     algo_inst = 0.0
     by_class = {}
     for k, pe in zip(keys, res_p["placements_executed"].tolist()):
         by_class[k] = by_class.get(k, 0) + pe
     for k, pe in by_class.items():
-        algo_inst += pe * model_inst_per_placement(k)
+        algo_inst += pe * per_placement(k)
     info = eng.device_info()
     peaks = {}
     try:
@@ -299,23 +328,32 @@ def our_arm(a):
     issue_peak = info["sm_count"] * 4 * sm_max_mhz * 1e6
     achieved = algo_inst / (rollout_ms / 1e3)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    # HBM bytes of the rollout kernel: root state read per task + 8 B record per task
+    n_launches = n_depths * search.info()["n_classes"]
+    # HBM bytes a rollout task needs: its problem's tables (on a problem switch) + 8 B record
     n_tasks = float(res_p["rollouts_executed"].sum()) / 32.0
-    algo_bytes = n_tasks * (26 * 2 * 4 + 40 * 2 + 48 + 8)
+    algo_bytes = n_tasks * (128 + 8) + float(res_p["depth"].sum() + P) * 2400.0
     roofline = {
-        "bound": "issue", "kernel": "fs_rollout_kernel",
+        "bound": "issue",
+        "kernel": "fs_rollout_lanes_kernel" if lane_kernel else "fs_rollout_kernel",
         "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
-        "frac": achieved / issue_peak, "traffic": None,
+        "frac": achieved / issue_peak,
+        "traffic": MEASURED_LANE_DRAM_BYTES_PER_LAUNCH if lane_kernel else 98560.0,
+        "traffic_unit": "DRAM bytes per launch (ncu --set full, profiles/r1)",
+        "algorithmic_bytes_per_launch": algo_bytes / max(n_launches, 1),
         "peak_source": "SMs x 4 schedulers x sm_max_mhz (%s)" %
                        ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "nvidia-smi"),
+        "model": ("thread instructions per placement / 32 (lane-per-rollout)" if lane_kernel
+                  else "warp instructions per placement (warp-per-board)"),
         "rollout_kernel_ms_per_step": rollout_ms, "advance_kernel_ms_per_step": advance_ms,
         "rollout_kernel_share_of_step": rollout_ms / (rollout_ms + advance_ms),
-        "launches_per_step": {"rollout": n_depths * len(by_class), "advance": n_depths * len(by_class)},
-        "avg_rollout_launch_ms": rollout_ms / max(n_depths * len(by_class), 1),
+        "launches_per_step": {"rollout": n_launches, "advance": n_launches},
+        "avg_rollout_launch_ms": rollout_ms / max(n_launches, 1),
         "placements_executed_per_step": float(res_p["placements_executed"].sum()),
         "placements_per_s_kernel": float(res_p["placements_executed"].sum()) / (rollout_ms / 1e3),
-        "algorithmic_inst_per_placement": {k: model_inst_per_placement(k) for k in by_class},
-        "ncu_inst_per_placement_r1_v1": {k: MEASURED_INST_PER_PLACEMENT_V1.get(k) for k in by_class},
+        "algorithmic_inst_per_placement": {k: per_placement(k) for k in by_class},
+        "ncu_inst_per_placement": ({k: MEASURED_LANE_THREAD_INST.get(k, 0) / 32.0 for k in by_class}
+                                   if lane_kernel else
+                                   {k: MEASURED_INST_PER_PLACEMENT_V1.get(k) for k in by_class}),
         "hbm": {"algorithmic_gbs": algo_bytes / (rollout_ms / 1e3) / 1e9, "peak_gbs": hbm_peak,
                 "frac": algo_bytes / (rollout_ms / 1e3) / 1e9 / hbm_peak},
     }
@@ -411,7 +449,7 @@ def our_arm(a):
             "placements_executed_per_step": placements_exec,
             "placements_per_s": placements / sec_per_step,
             "rollouts_executed_per_s": rollouts_exec / sec_per_step,
-            "solved": int(solved), "solutions_verified": verified,
+            "solved": int(solved), "solutions_verified_rank0": verified,
             "problems_per_step": P * world, "wall_s_per_step": wall / a.steps,
             "clocks": clocks, "gpu_launches": int(launches),
             "roofline": roofline, "e2e": e2e, "strong": strong, "cpu_baseline": cpu,

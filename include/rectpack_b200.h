@@ -160,6 +160,11 @@ int bp_search_step_reduce(bp_search *s);
 int bp_search_step_commit(bp_search *s, const void *gathered_stats_dev);
 int bp_search_stats_buffer(bp_search *s, void **stats_dev, int64_t *n_bytes);
 int bp_search_max_depth(bp_search *s, int *max_depth);
+/* lane_kernel = 1: rollouts run in the lane-per-rollout kernel (32 rollouts per warp, needs
+ * empty initial boards), 0: in the warp-per-board kernel (any initial board; also forced by
+ * the environment variable BP_ROLLOUT=warp).  n_classes = shape classes in the batch, each
+ * with its own launch sequence. */
+int bp_search_info(bp_search *s, int *lane_kernel, int *n_classes);
 /* synchronises the stream and copies results to the host
  *   results      : bp_search_result[n_problems]
  *   order        : NULL or uint8[n_problems][entry_stride / 2 + 2][2]  solution_tiles_order

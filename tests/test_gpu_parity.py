@@ -350,3 +350,38 @@ def test_full_size_properties(eng):
             assert r1["score"][i] == 20 - r1["depth"][i] >= 1
     # published G solve rate at N=1000/max_depth is 40.3 %; n = 200 gives +-7 points at 95 %
     assert 0.25 <= solved / 200.0 <= 0.55
+
+
+def _two_sample_z(k1, n1, k2, n2):
+    p = (k1 + k2) / float(n1 + n2)
+    se = (p * (1 - p) * (1.0 / n1 + 1.0 / n2)) ** 0.5
+    return abs(k1 / float(n1) - k2 / float(n2)) / se if se > 0 else 0.0
+
+
+@pytest.mark.parametrize("set_name,strategy,n_sim", [
+    ("g", "max_depth", 100), ("g", "max_depth", 1000), ("g", "avg_depth", 1000),
+    ("g", "max_depth", 5000), ("b", "avg_depth", 1000), ("b", "avg_depth", 5000)])
+def test_solve_rates_match_published(eng, golden, set_name, strategy, n_sim):
+    """Full 1000-problem sets at the reference's N: the solve rate must agree with the
+    published csv_results (tests/golden/published.json) within a two-sample binomial test
+    at 99.9 % (|z| < 3.29; n = 1000 on each side), every solution replays, and the mean
+    search effort (n_tiles_placed) is within 5 % of the published mean."""
+    from visapi_b200 import datasets
+    from visapi_b200.verify import replay_solution
+    pub = golden("published.json")[set_name]["%s/%d" % (strategy, n_sim)]
+    probs = datasets.load_problem_set(set_name)
+    batch = datasets.batch_arrays(probs)
+    res = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim,
+                          strategy=0 if strategy == "max_depth" else 1, seed=123)
+    solved = int(res["solution_found"].sum())
+    for i in np.flatnonzero(res["solution_found"]):
+        p = probs[i]
+        ok, why = replay_solution(p.rows, p.cols, p.tiles, res["order"][i, :res["n_order"][i]].tolist())
+        assert ok, (i, why)
+    z = _two_sample_z(solved, len(probs), pub["solved"], pub["n"])
+    assert z < 3.29, (solved, pub["solved"], z)
+    effort = float(res["n_tiles_placed"].mean())
+    assert abs(effort - pub["mean_n_tiles_placed"]) / pub["mean_n_tiles_placed"] < 0.05, (
+        effort, pub["mean_n_tiles_placed"])
+    score = float(res["score"].mean())
+    assert abs(score - pub["mean_score"]) < 0.15, (score, pub["mean_score"])

@@ -24,10 +24,18 @@ def cls_of(p):
     return "%d,%d,%d" % (rc((p.rows + 31) // 32), rc((p.cols + 31) // 32), rc((2 * len(p.tiles) + 31) // 32))
 
 
+def lanes_cls_of(p):
+    nb = 5 if p.rows <= 31 else (6 if p.rows <= 63 else (7 if p.rows <= 127 else 8))
+    w = 1 if p.cols <= 32 else (2 if p.cols <= 64 else 4)
+    ew = 2 if 2 * len(p.tiles) <= 64 else 4
+    return "%d,%d,%d" % (nb, w, ew)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--set", default="g")
-    ap.add_argument("--cls", default="1,1,2", help="RHO,W,EJ or 'all'")
+    ap.add_argument("--cls", default="all", help="warp class RHO,W,EJ or 'all'")
+    ap.add_argument("--lcls", default="all", help="lane class NB,W,EW or 'all'")
     ap.add_argument("--n-problems", type=int, default=200)
     ap.add_argument("--n-sim", type=int, default=1000)
     ap.add_argument("--strategy", default="max_depth")
@@ -37,6 +45,8 @@ def main():
     probs = datasets.load_problem_set(a.set)
     if a.cls != "all":
         probs = [p for p in probs if cls_of(p) == a.cls]
+    if a.lcls != "all":
+        probs = [p for p in probs if lanes_cls_of(p) == a.lcls]
     probs = probs[:a.n_problems]
     batch = datasets.batch_arrays(probs)
     eng = Engine(0)
@@ -48,7 +58,7 @@ def main():
         s.run()
     rollout_ms, advance_ms, n_depths = s.profile()
     r = s.results()
-    print(json.dumps({"cls": a.cls, "problems": len(probs), "n_sim": a.n_sim,
+    print(json.dumps({"cls": a.cls, "lcls": a.lcls, "problems": len(probs), "n_sim": a.n_sim,
                       "placements_executed": int(r["placements_executed"].sum()),
                       "rollouts_executed": int(r["rollouts_executed"].sum()),
                       "rollouts": int(r["rollouts"].sum()), "solved": int(r["solution_found"].sum()),

@@ -67,6 +67,7 @@ SYMBOLS = [
     ("bp_search_step_commit", C.c_int, [_vp, _vp]),
     ("bp_search_stats_buffer", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     ("bp_search_max_depth", C.c_int, [_vp, C.POINTER(C.c_int)]),
+    ("bp_search_info", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("bp_search_results", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("bp_search_destroy", C.c_int, [_vp]),
     ("bp_flat_search", C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int,
@@ -363,6 +364,11 @@ class Search(object):
     def step_commit(self, gathered_ptr=None):
         self.engine._check(self._lib.bp_search_step_commit(
             self._h, C.c_void_p(int(gathered_ptr)) if gathered_ptr else None))
+
+    def info(self):
+        lanes, ncls = C.c_int(), C.c_int()
+        self.engine._check(self._lib.bp_search_info(self._h, C.byref(lanes), C.byref(ncls)))
+        return {"lane_kernel": bool(lanes.value), "n_classes": ncls.value}
 
     def stats_buffer(self):
         ptr, nbytes = C.c_void_p(), C.c_int64()

@@ -1117,6 +1117,14 @@ int bp_search_stats_buffer(bp_search* s, void** stats_dev, int64_t* n_bytes)
     return BP_OK;
 }
 
+int bp_search_info(bp_search* s, int* lane_kernel, int* n_classes)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    if (lane_kernel) *lane_kernel = s->p.use_lanes;
+    if (n_classes) *n_classes = (int)s->classes.size();
+    return BP_OK;
+}
+
 int bp_search_max_depth(bp_search* s, int* max_depth)
 {
     BP_REQUIRE(s && max_depth, "null argument");
