@@ -86,7 +86,7 @@ def parse_args():
     ap.add_argument("--seed", type=int, default=123)
     ap.add_argument("--cpu-budget", type=float, default=15.0,
                     help="seconds of the python-port CPU sample (0 = skip cpu_baseline)")
-    ap.add_argument("--ref-budget", type=float, default=20.0,
+    ap.add_argument("--ref-budget", type=float, default=10.0,
                     help="--impl reference: seconds per step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
@@ -121,7 +121,7 @@ def reference_arm(a):
     samples = []
     base = None
     for i in range(a.warmup + a.steps):
-        base = run_cpu_baseline(a, a.ref_budget if i >= a.warmup else min(a.ref_budget, 3.0),
+        base = run_cpu_baseline(a, a.ref_budget if i >= a.warmup else min(a.ref_budget, 2.0),
                                 c_problems=8 if i == a.warmup + a.steps - 1 else 0)
         if i >= a.warmup:
             samples.append(base["python_port"])

@@ -277,3 +277,36 @@ def test_batched_mcts_equals_single(golden):
     for k, mv in enumerate(moves):
         assert probs[k].tolist() == mv["probs"]
     assert bm.leaf_batches <= g["num_sims"]
+
+
+def test_coach_episode_and_batched_selfplay(tmp_path):
+    """f2: an episode through the reference-shaped Coach and 8 lock-step games through
+    BatchedSelfPlay, both on the device tree with a PyTorch net; every example is labelled
+    with its episode's reward and the policy targets are distributions over valid moves."""
+    from visapi_b200.coach import BatchedSelfPlay, Coach
+    from visapi_b200.game import BinPackGame
+    from visapi_b200.nnet import TorchBinPackNet
+    np.random.seed(0)
+    game = BinPackGame(8, 8, 6)
+    net = TorchBinPackNet(game, epochs=1)
+    args = {"numMCTSSims": 12, "cpuct": 1.0, "tempThreshold": 3, "numIters": 1, "numEps": 2,
+            "checkpoint": str(tmp_path)}
+    coach = Coach(game, net, args)
+    ex = coach.executeEpisode()
+    assert 1 <= len(ex) <= 6
+    for grid, tiles, pi, r in ex:
+        assert grid.shape == (8, 8) and tiles.shape == (12, 2)
+        assert abs(sum(pi) - 1.0) < 1e-9 and 0 < r <= 1
+        valid = game.getValidMoves((grid, tiles), 1)
+        assert all(p == 0 for p, v in zip(pi, valid) if not v)
+    losses = coach.learn()
+    assert len(losses) == 1 and np.isfinite(losses[0])
+    assert (tmp_path / "best.pth.tar").exists()
+    sp = BatchedSelfPlay(8, 8, 6, net, args, n_games=8, seed=1)
+    examples, reward, searches = sp.play()
+    assert len(reward) == 8 and ((reward > 0) & (reward <= 1)).all()
+    assert len(examples) >= 8 and searches >= 8 * 12
+    assert sp.leaf_batches <= searches            # leaves of all games share a batch
+    for grid, tiles, pi, r in examples:
+        assert abs(pi.sum() - 1.0) < 1e-9
+    assert np.isfinite(net.train(examples))
