@@ -101,13 +101,11 @@ class BatchedSelfPlay(object):
         self.num_sims = int(_arg(args, 'numMCTSSims', 50))
         self.search = BatchedMCTS(
             height, width, 2 * n_tiles, self._predict, self.num_sims, float(_arg(args, 'cpuct', 1.0)),
-            self.B, device=device)
-        self._tiles_now = None
+            self.B, device=device, with_tiles=True)
         self.leaf_batches = 0
 
-    def _predict(self, grids):
-        # the leaf's tile list is what the tree returned with the grid
-        return self.nnet.predict_batch(grids, None)
+    def _predict(self, grids, tiles):
+        return self.nnet.predict_batch(grids, tiles)
 
     def play(self):
         """-> (examples, rewards [B], searches) ; examples as Coach.executeEpisode makes them."""

@@ -110,7 +110,7 @@ class BatchedMCTS(object):
     (pi [B', 2n], v [B'])`` is called once per simulation on the leaves of all trees."""
 
     def __init__(self, height, width, n_actions, predict_batch, num_sims, cpuct, n_trees,
-                 max_nodes=None, device=None):
+                 max_nodes=None, device=None, with_tiles=False):
         self.height, self.width, self.n_actions = height, width, n_actions
         self.predict_batch = predict_batch
         self.num_sims, self.B = int(num_sims), int(n_trees)
@@ -120,6 +120,7 @@ class BatchedMCTS(object):
                           cpuct)
         self.leaf_evals = 0
         self.leaf_batches = 0
+        self.with_tiles = with_tiles       # predict_batch(grids, tiles) instead of (grids)
 
     def set_roots(self, grids, tile_tables):
         """grids [B, H, W] (non-zero = occupied); tile_tables [B, 2n, 2]."""
@@ -134,7 +135,10 @@ class BatchedMCTS(object):
             need = np.flatnonzero(status == 0)
             if need.size:
                 grids = unpack_occupancy(occ[need], self.width).astype(np.float32)
-                pi, v = self.predict_batch(grids)
+                if self.with_tiles:
+                    pi, v = self.predict_batch(grids, tiles[need].astype(np.float32))
+                else:
+                    pi, v = self.predict_batch(grids)
                 pi = np.asarray(pi, dtype=np.float64)
                 for k, i in enumerate(need):
                     priors[i] = _mask_and_normalise(pi[k], valid[i].astype(np.float64))
