@@ -154,7 +154,8 @@ class BatchedMCTS(object):
             probs[np.arange(self.B), counts.argmax(axis=1)] = 1
             return probs
         c = counts ** (1. / temp)
-        return c / c.sum(axis=1, keepdims=True)
+        total = c.sum(axis=1, keepdims=True)
+        return np.divide(c, total, out=np.zeros_like(c), where=total > 0)   # finished games: zeros
 
     def root_counts_dev(self):
         return self._tree.root_counts_dev()
