@@ -98,7 +98,9 @@ def workload_config(a):
     return {"workload": "problems_%s[0:%d] 20-tile instances, flat MC search, N=%d rollouts/child, %s"
                         % (a.set, a.n_problems, a.n_sim, a.strategy),
             "set": a.set, "n_problems": a.n_problems, "n_sim": a.n_sim, "strategy": a.strategy,
-            "seed": a.seed, "l2": "none needed: a step streams no input; state lives in registers"}
+            "seed": a.seed,
+            "l2": "flushed between timed steps (256 MiB device memset); a step streams no input, "
+                  "rollout state lives in registers"}
 
 
 # ------------------------------------------------------------------ reference arm
@@ -243,7 +245,10 @@ def our_arm(a):
     search = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], a.n_sim,
                         strat, a.seed, streams)
 
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB of L2
+
     def step():
+        flush_buf.zero_()
         search.reset()
         search.run()
 
@@ -372,6 +377,7 @@ def our_arm(a):
         t0 = time.perf_counter()
         e2e_rollouts = 0.0
         for _ in range(a.steps):
+            flush_buf.zero_()
             r = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"],
                                 a.n_sim, strat, a.seed, streams)
             e2e_rollouts += float(r["rollouts"].sum())
@@ -402,6 +408,7 @@ def our_arm(a):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
         for _ in range(a.steps):
+            flush_buf.zero_()
             s2.reset()
             s2.run()
         e1.record(stream)
