@@ -126,16 +126,11 @@ def test_custom_mcts_predict_golden(golden):
             got = [ch.score for ch in node.children]
             exp = [(len(node.tiles) / 2 - 1) if s == "S" else s for s in want[d]]
             assert got == exp, (c["name"], d)
-            committed = [ch for ch in node.children if ch.children or ch is node.children[0]]
-            nxt = None
-            if d < depth:
-                # follow the committed child: the one whose board leads on
-                idx = [i for i, ch in enumerate(node.children)]
-                scores = [ch.score for ch in node.children]
-                nxt = node.children[scores.index(max(scores))]
-            if nxt is None:
+            if d >= depth:
                 break
-            node = nxt
+            # the committed child is the first one with the greatest score (get_max_index)
+            scores = [ch.score for ch in node.children]
+            node = node.children[scores.index(max(scores))]
         if found:
             base = [tuple(t) for t in c["tiles"]]
             half = []

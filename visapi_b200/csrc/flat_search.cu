@@ -358,7 +358,8 @@ __device__ __forceinline__ ChildStats stats_from_records(const SearchParams& p, 
     st.first_solved = NONE_U32;
     st.sum_steps = 0;
     st.prefix_steps = 0;
-    for (int ch = 0; ch < p.n_chunks; ++ch) {
+#pragma unroll 8
+    for (int ch = 0; ch < p.n_chunks; ++ch) {          // independent 8-byte loads, 8 in flight
         const ChunkRec r = rec[ch];
         st.max_steps = max(st.max_steps, (int)r.max_steps);
         st.sum_steps += r.sum_steps;
