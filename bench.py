@@ -334,6 +334,7 @@ def our_arm(a):
     achieved = algo_inst / (rollout_ms / 1e3)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     n_launches = n_depths * search.info()["n_classes"]
+    alu_only, alu_fma = eng.issue_microbench()
     # HBM bytes a rollout task needs: its problem's tables (on a problem switch) + 8 B record
     n_tasks = float(res_p["rollouts_executed"].sum()) / 32.0
     algo_bytes = n_tasks * (128 + 8) + float(res_p["depth"].sum() + P) * 2400.0
@@ -347,6 +348,8 @@ def our_arm(a):
         "algorithmic_bytes_per_launch": algo_bytes / max(n_launches, 1),
         "peak_source": "SMs x 4 schedulers x sm_max_mhz (%s)" %
                        ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "nvidia-smi"),
+        "measured_issue_gwarp_inst_s": {"lop3_iadd3_alu_pipe_only": alu_only,
+                                        "lop3_imad_alu_plus_fma": alu_fma},
         "model": ("thread instructions per placement / 32 (lane-per-rollout)" if lane_kernel
                   else "warp instructions per placement (warp-per-board)"),
         "rollout_kernel_ms_per_step": rollout_ms, "advance_kernel_ms_per_step": advance_ms,

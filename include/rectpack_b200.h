@@ -70,6 +70,12 @@ int bp_synchronize(bp_context *ctx);
 /* sm_count, max SM clock (kHz), kernels launched by this context so far */
 int bp_device_info(bp_context *ctx, int *sm_count, int *sm_clock_khz, int64_t *kernel_launches);
 
+/* Issue-rate micro-benchmark (measurement aid): G warp-instructions/s of a
+ * dependency-free LOP3/IADD3 stream (ALU pipe only) and of a LOP3/IMAD stream (ALU + FMA
+ * pipes) on every SM.  The roofline peak of bench.py is SMs x 4 x clock; these two numbers
+ * show how much of it integer code can reach. */
+int bp_issue_microbench(bp_context *ctx, double *alu_only_ginst, double *alu_fma_ginst);
+
 /* ---- a1: search.find_first (engine/search.f90:1-16) ----------------------------- */
 /* first 0-based index k with haystack[k] == needle, else -1 */
 int bp_find_first(bp_context *ctx, int32_t needle, const int32_t *haystack, int64_t n,

@@ -46,6 +46,7 @@ SYMBOLS = [
     ("bp_set_stream", C.c_int, [_vp, _vp]),
     ("bp_synchronize", C.c_int, [_vp]),
     ("bp_device_info", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(_i64)]),
+    ("bp_issue_microbench", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     ("bp_find_first", C.c_int, [_vp, _i32, _vp, _i64, C.POINTER(_i64)]),
     ("bp_lfb", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, _vp, _vp]),
     ("bp_valid_masks", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, _vp, _vp, _vp]),
@@ -200,6 +201,12 @@ class Engine(object):
         sm, khz, launches = C.c_int(), C.c_int(), C.c_int64()
         self._check(self._lib.bp_device_info(self._h, C.byref(sm), C.byref(khz), C.byref(launches)))
         return {"sm_count": sm.value, "sm_clock_khz": khz.value, "kernel_launches": launches.value}
+
+    def issue_microbench(self):
+        """G warp-instructions/s of dependency-free integer streams: (ALU only, ALU + FMA)."""
+        a, b = C.c_double(), C.c_double()
+        self._check(self._lib.bp_issue_microbench(self._h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     @property
     def kernel_launches(self):

@@ -252,6 +252,39 @@ rollouts_kernel(int n_roots, int rows, int cols, int wpr, int n_entries,
     }
 }
 
+// ------------------------------------------------------- issue-rate micro-benchmark
+// Dependency-free integer streams: 8 chains per thread, each step one instruction per chain
+// whose second operand is the neighbouring chain (so steps cannot be folded together):
+// ALU mode = 8 LOP3 per step (ALU pipe only), MIXED mode = 4 LOP3 + 4 IMAD (ALU + FMA pipes).
+// Measures what "issue peak" means for integer code on this chip.
+template <bool MIXED>
+__global__ void __launch_bounds__(256) issue_microbench_kernel(uint32_t* out, int iters, uint32_t seed)
+{
+    uint32_t a[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) a[i] = seed + threadIdx.x * 8u + i;
+    const uint32_t k1 = (seed | 1u) + (threadIdx.x << 8);      // per-thread: a register operand
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int r = 0; r < 8; ++r) {
+            uint32_t n[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (MIXED && (i & 1))                                           // IMAD
+                    asm volatile("mad.lo.u32 %0, %1, %2, %3;" : "=r"(n[i]) : "r"(a[i]), "r"(k1), "r"(a[(i + 1) & 7]));
+                else                                                            // LOP3: (a & k1) ^ b
+                    asm volatile("lop3.b32 %0, %1, %2, %3, 0x6a;" : "=r"(n[i]) : "r"(a[(i + 1) & 7]), "r"(a[i]), "r"(k1));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] = n[i];
+        }
+    }
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) x ^= a[i];
+    if (x == 0xDEADBEEFu) out[0] = x;                             // keep the chains alive
+}
+
 }  // namespace bp
 
 // =================================================================== C ABI
@@ -316,6 +349,41 @@ int bp_device_info(bp_context* ctx, int* sm_count, int* sm_clock_khz, int64_t* k
     if (sm_count) *sm_count = ctx->sm_count;
     if (sm_clock_khz) *sm_clock_khz = ctx->sm_clock_khz;
     if (kernel_launches) *kernel_launches = ctx->launches;
+    return BP_OK;
+}
+
+int bp_issue_microbench(bp_context* ctx, double* alu_only_ginst, double* alu_fma_ginst)
+{
+    BP_REQUIRE(ctx && alu_only_ginst && alu_fma_ginst, "null argument");
+    BP_CUDA(cudaSetDevice(ctx->device));
+    int rc = ensure_scratch(ctx, 1024);
+    if (rc) return rc;
+    uint32_t* d_out = static_cast<uint32_t*>(ctx->scratch);
+    const int iters = 2000, grid = ctx->sm_count * 8, block = 256;
+    cudaEvent_t e0, e1;
+    BP_CUDA(cudaEventCreate(&e0));
+    BP_CUDA(cudaEventCreate(&e1));
+    double res[2] = {0.0, 0.0};
+    for (int mode = 0; mode < 2; ++mode) {
+        for (int rep = 0; rep < 3; ++rep) {                       // the last repetition is timed
+            BP_CUDA(cudaEventRecord(e0, ctx->stream));
+            if (mode == 0) issue_microbench_kernel<false><<<grid, block, 0, ctx->stream>>>(d_out, iters, 12345u);
+            else issue_microbench_kernel<true><<<grid, block, 0, ctx->stream>>>(d_out, iters, 12345u);
+            BP_CUDA(cudaEventRecord(e1, ctx->stream));
+            BP_CUDA(cudaEventSynchronize(e1));
+            ctx->launches++;
+        }
+        float ms = 0.f;
+        BP_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+        // 8 chains x 8 repeats = 64 instructions per iteration per warp
+        const double warp_inst = (double)grid * (block / 32) * (double)iters * 64.0;
+        res[mode] = warp_inst / (ms * 1e-3) / 1e9;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    BP_CUDA(cudaGetLastError());
+    *alu_only_ginst = res[0];
+    *alu_fma_ginst = res[1];
     return BP_OK;
 }
 
