@@ -174,6 +174,9 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     __shared__ uint32_t s_hmask[4][HROWS * EW];
     __shared__ __align__(16) uint32_t s_groups[4][NE * 2 * EW];
     __shared__ uint2 s_tile[4][NE];
+    __shared__ uint8_t s_sel8[256 * 8];
+    fill_select_table(s_sel8);
+    __syncthreads();
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const unsigned n_children = p.child_count[depth_slot * FS_CLASSES + cls];
@@ -241,8 +244,8 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
         const int count = min(CHUNK, p.n_local - first);
         int my_solved;
         const int my_steps = lanes_rollout<NB, W, EW>(
-            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_groups[warp], s_tile[warp], p.seed,
-            d.stream, tag,
+            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_groups[warp], s_tile[warp], s_sel8,
+            p.seed, d.stream, tag,
             (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
 
         const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved != 0);

@@ -68,6 +68,30 @@ __device__ __forceinline__ int select_bit32(uint32_t m, int k)
     return pos;
 }
 
+// Same through a 2 KB shared-memory table: sel8[b * 8 + k] = position of the k-th set bit of
+// byte b.  Three independent popcounts (XU pipe) pick the byte, one LDS (LSU pipe) finishes:
+// fewer ALU-pipe instructions than the binary select, and the ALU pipe is what binds the kernel.
+__device__ __forceinline__ int select_bit32_lut(uint32_t m, int k, const uint8_t* __restrict__ sel8)
+{
+    const int c0 = __popc(m & 0xFFu), c1 = __popc(m & 0xFFFFu), c2 = __popc(m & 0xFFFFFFu);
+    const int byte = (k >= c0) + (k >= c1) + (k >= c2);
+    const int pre = (k >= c2) ? c2 : ((k >= c1) ? c1 : ((k >= c0) ? c0 : 0));
+    const uint32_t b = (m >> (8 * byte)) & 0xFFu;
+    return 8 * byte + (int)sel8[b * 8 + (k - pre)];
+}
+
+// fill sel8[256 * 8] (call with all threads of the block, then __syncthreads)
+__device__ __forceinline__ void fill_select_table(uint8_t* sel8)
+{
+    for (int b = threadIdx.x; b < 256; b += blockDim.x) {
+        int k = 0;
+#pragma unroll
+        for (int bit = 0; bit < 8; ++bit)
+            if ((b >> bit) & 1) sel8[b * 8 + k++] = (uint8_t)bit;
+        for (; k < 8; ++k) sel8[b * 8 + k] = 0;
+    }
+}
+
 // clear the lowest set bit of (alive & group); returns false if there is none
 template <int EW>
 __device__ __forceinline__ bool kill_lowest(uint32_t (&alive)[EW], const uint32_t* group)
@@ -133,7 +157,8 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                                              const uint32_t* __restrict__ wmask,
                                              const uint32_t* __restrict__ hmask,
                                              const uint32_t* __restrict__ groups,
-                                             const uint2* __restrict__ tile, uint32_t seed,
+                                             const uint2* __restrict__ tile,
+                                             const uint8_t* __restrict__ sel8, uint32_t seed,
                                              uint32_t stream, uint32_t tag, uint32_t sim, int active,
                                              int& solved)
 {
@@ -213,7 +238,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         m = past ? legal[q] : m;
                         base = past ? 32 * q : base;
                     }
-                    const int e = base + select_bit32(m, idx);
+                    const int e = base + select_bit32_lut(m, idx, sel8);
                     const uint2 t = tile[e];                                // (h | w << 8, (1 << w) - 1)
                     const int th = (int)(t.x & 0xFFu), tw = (int)(t.x >> 8);
                     if (W == 1) {
