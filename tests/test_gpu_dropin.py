@@ -305,3 +305,24 @@ def test_coach_episode_and_batched_selfplay(tmp_path):
     for grid, tiles, pi, r in examples:
         assert abs(pi.sum() - 1.0) < 1e-9
     assert np.isfinite(net.train(examples))
+
+
+def test_run_mcts_command(tmp_path, capsys):
+    """manage.py run_mcts, DB-free: generated instances and --from_file, results CSV in the
+    reference's csv_results schema, every reported solution verified by the command itself."""
+    import csv
+    from visapi_b200 import run_mcts
+    out = tmp_path / "results.csv"
+    run_mcts.main(["20", "11", "11", "--n_sim", "50", "--count", "3", "--both_strategies",
+                   "--out", str(out), "--quiet"])
+    run_mcts.main(["20", "0", "0", "--from_file", "--set", "g", "--limit", "16", "--n_sim", "100",
+                   "--avg_depth", "--out", str(out), "--quiet"])
+    text = capsys.readouterr().out
+    assert "solved (every solution replayed and verified)" in text
+    rows = list(csv.DictReader(open(out), delimiter=";"))
+    assert len(rows) == 3 * 2 + 16
+    assert set(rows[0]) == {"rows", "cols", "tiles", "n_tiles", "strategy", "n_simulations", "score",
+                            "solution_found", "n_tiles_placed", "created_on"}
+    assert all(r["n_tiles"] == "20" for r in rows)
+    assert {r["strategy"] for r in rows} == {"max_depth", "avg_depth"}
+    assert all(int(r["n_tiles_placed"]) > 0 for r in rows)

@@ -1156,19 +1156,23 @@ int bp_search_run(bp_search* s)
         set_error("bp_search_run: call bp_search_reset first");
         return BP_ERR_STATE;
     }
-    // fork: every class runs its whole depth loop on its own stream, then join
+    // fork: every class runs its whole depth loop on its own stream, then join.  Launches are
+    // issued depth-major (all classes' depth 0, then depth 1, ...) so that every chain starts
+    // at once instead of waiting for the host to issue the chains before it.
     BP_CUDA(cudaSetDevice(s->ctx->device));
     BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
-    for (size_t k = 0; k < s->classes.size(); ++k) {
-        const int c = s->classes[k];
-        cudaStream_t st = s->cls_stream[k];
-        BP_CUDA(cudaStreamWaitEvent(st, s->fork_ev, 0));
-        for (int d = 0; d < s->cls_depth[k]; ++d) {
-            launch_rollouts_class(s, c, d, st);
-            launch_advance_class<false>(s, c, d + 1, nullptr, st);
+    for (size_t k = 0; k < s->classes.size(); ++k)
+        BP_CUDA(cudaStreamWaitEvent(s->cls_stream[k], s->fork_ev, 0));
+    for (int d = 0; d < s->max_depth; ++d) {
+        for (size_t k = 0; k < s->classes.size(); ++k) {
+            if (d >= s->cls_depth[k]) continue;
+            launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k]);
+            launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
         }
-        BP_CUDA(cudaGetLastError());
-        BP_CUDA(cudaEventRecord(s->cls_done[k], st));
+    }
+    BP_CUDA(cudaGetLastError());
+    for (size_t k = 0; k < s->classes.size(); ++k) {
+        BP_CUDA(cudaEventRecord(s->cls_done[k], s->cls_stream[k]));
         BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->cls_done[k], 0));
     }
     s->cur_depth = s->max_depth;
