@@ -1,124 +1,116 @@
-"""Search-tree node (reference: engine/state.py:63-153) and its JSON / dict renderers."""
+"""Search-tree node of the flat Monte-Carlo search and its exports.
+
+Interface of the reference's ``State`` (engine/state.py:63-153): the attributes callers
+touch (``board``, ``tiles``, ``parent``, ``children``, ``score``, ``tile_placed``,
+``solution_tiles_order``, ``uuid``) and the renderers the Django view layer consumes
+(``render_to_json``, ``render_children``, ``to_json``).  On the device a state is never an
+object: it is a packed board plus a tile table; these nodes are built
+on the host from the per-depth child scores a search returns (mcts.CustomMCTS._rebuild_tree).
+"""
+import itertools
 from collections import OrderedDict
 
 import numpy as np
 
 ORIENTATIONS = 2
 
-
-class _Counter(object):
-    def __init__(self):
-        self.i = 0
-
-    def uuid(self):
-        self.i += 1
-        return self.i
+_ids = itertools.count(1)
 
 
-_uuid = _Counter()
-
-
-def sort_key(x):
-    return x.score
+def sort_key(node):
+    return node.score
 
 
 class State(object):
-    """board is copied (np.copy) and tiles is sliced on construction, as the reference
-    does (state.py:66-67), so a State never aliases its parent's board."""
 
     def __init__(self, board, tiles, parent=None, solution_tiles_order=None):
-        self.board = np.copy(board)
-        self.tiles = tiles[:]
+        # a node owns private copies: callers mutate boards in place (destroy_state=True)
+        self.board = np.array(board, copy=True)
+        self.tiles = list(tiles)
         self.parent = parent
-        self.uuid = _uuid.uuid()
+        self.uuid = next(_ids)
         self.children = []
         self.score = None
         self.tile_placed = None
-        if parent and parent.solution_tiles_order:
-            self.solution_tiles_order = parent.solution_tiles_order
-        else:
-            self.solution_tiles_order = []
+        inherited = getattr(parent, "solution_tiles_order", None) if parent is not None else None
+        self.solution_tiles_order = inherited if inherited else []
 
+    # ---- identity / navigation ---------------------------------------------------------
     def uuid_str(self):
-        return '%s' % self.uuid
+        return str(self.uuid)
 
     def copy(self):
+        """Fresh node (new uuid, no children) over copies of this board and tile list."""
         return State(self.board, self.tiles, parent=self.parent)
 
     def child_with_biggest_score(self):
-        return sorted(self.children, key=sort_key, reverse=True)[0]
-
-    def to_json(self):
-        return {
-            'tiles': self.tiles,
-            'board': self.board.tolist(),
-            'tile_placed': self.tile_placed,
-            'score': self.score or 0,
-            'name': self.uuid_str(),
-            'children': [],
-        }
-
-    def render_to_json(self):
-        return render_to_json(self)
-
-    def render_children(self, only_ids=False):
-        ret, all_nodes = render_to_dict(self, all_nodes={}, only_ids=only_ids)
-        self_str = self.uuid_str() if only_ids else str(self)
-        all_nodes[self.uuid_str()] = self
-        return {self_str: ret}, all_nodes
+        return max(self.children, key=sort_key)
 
     def centralize_node_with_children(self):
-        """Moves the child that has children to the middle slot, level by level
-        (state.py:116-136; used for the tree visualisation)."""
-        _state = self
-        while _state.children:
-            index_with_children = None
-            for i, child in enumerate(_state.children):
-                if child.children:
-                    index_with_children = i
-            if index_with_children is None:
-                break
-            n = len(_state.children)
-            middle = n // 2 - 1 if n % 2 == 0 else n // 2
-            nxt = _state.children[index_with_children]
-            kids = _state.children
-            kids[middle], kids[index_with_children] = kids[index_with_children], kids[middle]
-            _state = nxt
+        """Along the path of expanded nodes, move the expanded child of every node to the
+        middle slot of its sibling list (engine/state.py:116-136; tree drawing only)."""
+        node = self
+        while node.children:
+            expanded = [i for i, child in enumerate(node.children) if child.children]
+            if not expanded:
+                return
+            src = expanded[-1]
+            mid = (len(node.children) - 1) // 2
+            follow = node.children[src]
+            node.children[mid], node.children[src] = node.children[src], node.children[mid]
+            node = follow
 
-    def __str__(self):
-        return self.__repr__()
+    # ---- exports ------------------------------------------------------------------------
+    def to_json(self):
+        return OrderedDict([
+            ('tiles', self.tiles),
+            ('board', self.board.tolist()),
+            ('tile_placed', self.tile_placed),
+            ('score', self.score if self.score else 0),
+            ('name', self.uuid_str()),
+            ('children', []),
+        ])
+
+    def render_to_json(self):
+        """Nested {'name', 'board', 'tiles', 'score', 'tile_placed', 'children': [...]}."""
+        out = self.to_json()
+        out['children'] = [child.render_to_json() for child in self.children]
+        return out
+
+    def render_children(self, only_ids=False):
+        """({label: {child label: {...}}}, {uuid: node}) with uuid or text labels."""
+        index = {}
+
+        def label(node):
+            return node.uuid_str() if only_ids else str(node)
+
+        def walk(node):
+            index[node.uuid_str()] = node
+            return OrderedDict((label(child), walk(child)) for child in node.children)
+
+        return {label(self): walk(self)}, index
 
     def __repr__(self, short=False):
         if short:
-            return '%s' % (self.tiles,)
-        output_list = [list(x) for x in self.tiles]
-        if len(output_list) > 6:
-            output_list = str(output_list[:6]) + '(...)'
-        output_board = ''
-        if len(self.tiles) <= 4:
-            output_board = self.board
-        return ('(%s) Remaining tiles: %s, Tile placed: %s. Tiles: %s. Sim. depth:(%s) %s' % (
-            self.uuid, len(self.tiles) / ORIENTATIONS, self.tile_placed, output_list, self.score,
-            output_board))
+            return str(self.tiles)
+        shown = [list(t) for t in self.tiles]
+        if len(shown) > 6:
+            shown = '%s(...)' % (shown[:6],)
+        tail = self.board if len(self.tiles) <= 4 else ''
+        return '({}) Remaining tiles: {}, Tile placed: {}. Tiles: {}. Sim. depth:({}) {}'.format(
+            self.uuid, len(self.tiles) / ORIENTATIONS, self.tile_placed, shown, self.score, tail)
+
+    __str__ = __repr__
 
 
 def render_to_dict(node, tree=None, all_nodes=None, only_ids=False):
-    """Nested OrderedDict of the subtree plus {uuid: node} (state.py:16-43)."""
-    if all_nodes is None:
-        all_nodes = {}
-    all_nodes[node.uuid_str()] = node
-    if not node.children:
-        return {}, all_nodes
-    sub = OrderedDict()
-    for child in node.children:
-        key = child.uuid_str() if only_ids else str(child)
-        sub[key], all_nodes = render_to_dict(child, None, all_nodes, only_ids=only_ids)
-    return sub, all_nodes
+    """Function form kept for callers of the reference's module-level helper."""
+    nested, index = node.render_children(only_ids=only_ids)
+    if all_nodes is not None:
+        all_nodes.update(index)
+        index = all_nodes
+    return next(iter(nested.values())), index
 
 
-def render_to_json(node):
-    """{..., 'children': [...]} recursively (state.py:45-61)."""
-    out = node.to_json()
-    for child in node.children:
-        out['children'].append(render_to_json(child))
-    return out
+def render_to_json(node, tree=None, i=0, all_nodes=None, only_ids=False):
+    return node.render_to_json()
