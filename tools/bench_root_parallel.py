@@ -35,6 +35,11 @@ def instance(n, rows, cols, seed):
 
 
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--n-sim", type=int, default=5000)
+    ap.add_argument("--seeds", type=int, default=8)
+    a = ap.parse_args()
     from visapi_b200 import Engine, datasets, parallel
     from visapi_b200.verify import replay_solution
     rank = int(os.environ.get("RANK", "0"))
@@ -44,12 +49,12 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local, stream=torch.cuda.current_stream().cuda_stream)
-    n_sim = 5000
+    n_sim = a.n_sim
     out = {"world": world, "n_sim": n_sim, "boards": {}}
     digest = hashlib.sha256()
     for (rows, cols) in ((25, 25), (40, 40)):
         times, depths, found, rollouts = [], [], 0, 0
-        for seed in range(8):
+        for seed in range(a.seeds):
             p = instance(50, rows, cols, seed)
             batch = datasets.batch_arrays([p])
             for rep in range(2):                                  # second run is timed
