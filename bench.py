@@ -76,7 +76,7 @@ def lane_class_key(rows, cols, n_entries):
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--set", default="g", choices=["g", "b"])
@@ -154,7 +154,7 @@ def reference_arm(a):
 
 # ------------------------------------------------------------------ clocks
 class ClockSampler(object):
-    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+    QUERY = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
@@ -167,12 +167,22 @@ class ClockSampler(object):
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.QUERY,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=self.tmp, stderr=subprocess.DEVNULL)
         except OSError:
             self.proc = None
 
-    def stop(self):
+    @staticmethod
+    def _stamp(text):
+        import datetime
+        try:
+            return datetime.datetime.strptime(text.strip(), "%Y/%m/%d %H:%M:%S.%f").timestamp()
+        except ValueError:
+            return None
+
+    def stop(self, t_begin=None, t_end=None):
+        """Median SM clock and throttle reasons of the samples taken inside [t_begin, t_end]
+        (wall clock of the timed region); all samples when none fall inside."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -182,27 +192,31 @@ class ClockSampler(object):
             self.proc.kill()
         self.tmp.flush()
         self.tmp.seek(0)
-        sm, mx, reasons, power = [], [], set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        rows = []
         for line in self.tmp.read().splitlines():
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
-                power.append(float(f[3]))
+                rows.append((self._stamp(f[0]), float(f[1]), float(f[2]), float(f[3]),
+                             [n for n, v in zip(names, f[5:9]) if v.lower().startswith("active")]))
             except ValueError:
                 continue
-            for name, v in zip(names, f[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
+        inside = [r for r in rows if r[0] is not None and t_begin is not None and
+                  t_begin <= r[0] <= t_end]
+        use = inside if inside else rows
+        sm = [r[1] for r in use]
+        mx = [r[2] for r in use]
+        power = [r[3] for r in use]
+        reasons = set(n for r in use for n in r[4])
         self.tmp.close()
         os.unlink(self.tmp.name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "power_w_max": float(max(power)), "samples": len(sm), "reasons": sorted(reasons)}
+                "power_w_max": float(max(power)), "samples": len(sm),
+                "samples_inside_timed_region": len(inside), "reasons": sorted(reasons)}
 
 
 # ------------------------------------------------------------------ our arm
@@ -273,7 +287,7 @@ def our_arm(a):
     wall = time.time() - t_wall0
     launches = eng.kernel_launches - launches0
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop()
+    clocks = sampler.stop(t_wall0, t_wall0 + wall)
     res = search.results()
 
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
