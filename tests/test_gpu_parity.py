@@ -385,3 +385,30 @@ def test_solve_rates_match_published(eng, golden, set_name, strategy, n_sim):
         effort, pub["mean_n_tiles_placed"])
     score = float(res["score"].mean())
     assert abs(score - pub["mean_score"]) < 0.15, (score, pub["mean_score"])
+
+
+def test_full_n_exact_parity_with_oracle(eng):
+    """BASELINE's N = 1000 on whole problems: the CUDA flat search equals the C oracle
+    field for field (depth, found, n_tiles_placed, rollouts, solution order) on 48 G and
+    16 B instances, for both strategies on a subset."""
+    from visapi_b200 import datasets
+    for set_name, count, strategies in (("g", 48, ("max_depth", "avg_depth")), ("b", 16, ("avg_depth",))):
+        probs = datasets.load_problem_set(set_name)[:count]
+        batch = datasets.batch_arrays(probs)
+        for strategy in strategies:
+            sub = len(probs) if strategy == "max_depth" or set_name == "b" else 16
+            got = eng.flat_search(batch["rows"][:sub], batch["cols"][:sub], batch["tiles"][:sub],
+                                  batch["n_entries"][:sub], 1000,
+                                  strategy=0 if strategy == "max_depth" else 1, seed=123,
+                                  streams=np.arange(sub, dtype=np.uint32))
+            want = c_oracle.flat_search_batch(batch["rows"][:sub], batch["cols"][:sub],
+                                              batch["tiles"][:sub].astype(np.int32),
+                                              batch["n_entries"][:sub], 1000, strategy, 123,
+                                              np.arange(sub, dtype=np.uint32), n_threads=0)
+            for i, w in enumerate(want):
+                assert int(got["depth"][i]) == w["depth"], (set_name, strategy, i)
+                assert bool(got["solution_found"][i]) == w["solution_found"]
+                assert int(got["n_tiles_placed"][i]) == w["n_tiles_placed"]
+                assert int(got["rollouts"][i]) == w["rollouts"]
+                assert int(got["rollout_placements"][i]) == w["rollout_placements"]
+                assert got["order"][i, :got["n_order"][i]].tolist() == w["solution_tiles_order"]
