@@ -268,8 +268,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
 // tables the lane-per-rollout kernel reads, from the warp-per-board state of one problem
 template <int RHO, int W, int EJ>
 __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int prob, const ProblemDesc& d,
-                                                  const WarpState<RHO, W, EJ>& s, int n_alive,
-                                                  uint16_t* sh_ent /* [32*EJ] */)
+                                                  const WarpState<RHO, W, EJ>& s, int n_alive)
 {
     const int lane = lane_id();
     // ---- column heights, bit-sliced (every lane computes the same words) ----------------
@@ -330,7 +329,6 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
         for (int q = 1; q < 8; ++q) out = (lane == q) ? m[q] : out;
         if (lane < 8) gg[e * LANES_GROUP_WORDS + lane] = out;
     }
-    (void)sh_ent;
 
     // ---- wmask[x] = entries with w <= x, hmask[y] = entries with h <= y ------------------
     uint32_t* gw = p.wmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
@@ -625,7 +623,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
                     (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
             base += __popc(legal[j]);
         }
-        if (p.use_lanes) write_lane_tables(p, prob, d, s, n_alive, cbuf[warp]);
+        if (p.use_lanes) write_lane_tables(p, prob, d, s, n_alive);
     }
 }
 

@@ -56,21 +56,10 @@ __device__ __forceinline__ uint32_t word_range(int lo, int hi, int q)
     return (b > a) ? bit_range(a, b) : 0u;
 }
 
-// position of the k-th (0-based) set bit of m; k < popc(m)
-__device__ __forceinline__ int select_bit32(uint32_t m, int k)
-{
-    int pos = 0, t;
-    t = __popc(m & 0xFFFFu); if (k >= t) { k -= t; pos += 16; m >>= 16; }
-    t = __popc(m & 0xFFu);   if (k >= t) { k -= t; pos += 8;  m >>= 8; }
-    t = __popc(m & 0xFu);    if (k >= t) { k -= t; pos += 4;  m >>= 4; }
-    t = __popc(m & 0x3u);    if (k >= t) { k -= t; pos += 2;  m >>= 2; }
-    if (k >= (int)(m & 1u)) pos += 1;
-    return pos;
-}
-
-// Same through a 2 KB shared-memory table: sel8[b * 8 + k] = position of the k-th set bit of
-// byte b.  Three independent popcounts (XU pipe) pick the byte, one LDS (LSU pipe) finishes:
-// fewer ALU-pipe instructions than the binary select, and the ALU pipe is what binds the kernel.
+// Position of the k-th (0-based) set bit of m, k < popc(m), through a 2 KB shared-memory
+// table: sel8[b * 8 + k] = position of the k-th set bit of byte b.  Three independent
+// popcounts (XU pipe) pick the byte and one LDS (LSU pipe) finishes: fewer ALU-pipe
+// instructions than a five-level binary select, and the ALU pipe is what binds the kernel.
 __device__ __forceinline__ int select_bit32_lut(uint32_t m, int k, const uint8_t* __restrict__ sel8)
 {
     const int c0 = __popc(m & 0xFFu), c1 = __popc(m & 0xFFFFu), c2 = __popc(m & 0xFFFFFFu);
