@@ -317,6 +317,13 @@ def test_run_mcts_command(tmp_path, capsys):
                    "--out", str(out), "--quiet"])
     run_mcts.main(["20", "0", "0", "--from_file", "--set", "g", "--limit", "16", "--n_sim", "100",
                    "--avg_depth", "--out", str(out), "--quiet"])
+    run_mcts.main(["8", "6", "7", "--n_sim", "20", "--count", "2", "--quiet",
+                   "--dump_tree", str(tmp_path / "trees")])
+    import json
+    trees = sorted((tmp_path / "trees").glob("*_tree.json"))
+    assert len(trees) == 2
+    t = json.load(open(trees[0]))
+    assert t["tree"]["children"] and "board" in t["tree"] and "solution_tiles_order" in t
     text = capsys.readouterr().out
     assert "solved (every solution replayed and verified)" in text
     rows = list(csv.DictReader(open(out), delimiter=";"))

@@ -158,11 +158,32 @@ def pack_tiles(tile_lists, n_entries=None):
 
 
 # ------------------------------------------------------------------------ engine
+class _LockedLibrary(object):
+    """Serialises every call made through one context: the C ABI allows one caller at a time
+    per bp_context, and ctypes releases the GIL while a call runs."""
+
+    def __init__(self, lib, lock):
+        self._lib, self._lock = lib, lock
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        lock = self._lock
+
+        def locked(*args):
+            with lock:
+                return fn(*args)
+        locked.__name__ = name
+        setattr(self, name, locked)
+        return locked
+
+
 class Engine(object):
-    """One bp_context: a device plus the stream its kernels run on."""
+    """One bp_context: a device plus the stream its kernels run on.  Calls from several
+    Python threads are serialised by a per-engine lock."""
 
     def __init__(self, device=0, stream=None):
-        self._lib = load_library()
+        self._lock = threading.RLock()
+        self._lib = _LockedLibrary(load_library(), self._lock)
         handle = C.c_void_p()
         rc = self._lib.bp_create(int(device), C.byref(handle))
         if rc != 0:

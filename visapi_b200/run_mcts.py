@@ -45,6 +45,9 @@ def add_arguments(parser):
     parser.add_argument("--seed", type=int, default=123, help="Philox seed (reference: random.seed(123))")
     parser.add_argument("--both_strategies", action="store_true", help="run max_depth and avg_depth")
     parser.add_argument("--out", default=None, help="results CSV (reference results_*.csv schema)")
+    parser.add_argument("--dump_tree", default=None,
+                        help="directory for the per-problem search tree as JSON (State.render_to_json), "
+                             "as the reference stores in Result.result_tree")
     parser.add_argument("--quiet", action="store_true")
 
 
@@ -143,7 +146,39 @@ def run_mcts(options):
     print("wall %.3f s on %d GPU(s), device %s" % (dt, world, device))
     if options["out"]:
         datasets.write_results_csv(options["out"], rows_out, append=True)
+    if options.get("dump_tree"):
+        dump_trees(options, probs, strategies, device)
     return rows_out
+
+
+class _NpEncoder(json.JSONEncoder):
+    def default(self, obj):
+        if isinstance(obj, np.integer):
+            return int(obj)
+        if isinstance(obj, np.floating):
+            return float(obj)
+        if isinstance(obj, np.ndarray):
+            return obj.tolist()
+        return super(_NpEncoder, self).default(obj)
+
+
+def dump_trees(options, probs, strategies, device):
+    """One JSON file per (problem, strategy) with the tree CustomMCTS.predict builds: every
+    evaluated child of every depth with its score and board (run_mcts.py:227-239)."""
+    os.makedirs(options["dump_tree"], exist_ok=True)
+    for i, p in enumerate(probs):
+        for strategy in strategies:
+            m = CustomMCTS(p.entries(), p.board(), strategy=strategy, seed=options["seed"], stream=i,
+                           device=device)
+            root, depth, found = m.predict(N=options["n_sim"])
+            root.centralize_node_with_children()
+            name = "%d_%d_%d_%s_%d_%d_tree.json" % (len(p.tiles), p.cols, p.rows, strategy,
+                                                    options["n_sim"], i)
+            with open(os.path.join(options["dump_tree"], name), "w") as f:
+                json.dump({"depth": depth, "solution_found": found,
+                           "n_tiles_placed": m.n_tiles_placed,
+                           "solution_tiles_order": m.solution_tiles_order,
+                           "tree": root.render_to_json()}, f, cls=_NpEncoder)
 
 
 def main(argv=None):
