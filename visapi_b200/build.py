@@ -5,6 +5,7 @@
 The shared library is git-ignored but travels to the GPU box with the snapshot.
 """
 import concurrent.futures
+import hashlib
 import os
 import shutil
 import subprocess
@@ -40,9 +41,28 @@ def _sources():
     return [s for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def source_hash():
+    """Digest of every source the library is built from (and of the flags): the library is
+    rebuilt when this changes, not when file times do — a snapshot copied to the GPU box keeps
+    its prebuilt .so even if the copy reset the mtimes."""
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for name in sorted(_sources()) + sorted(HEADERS + ["lanes.cuh"]):
+        path = os.path.join(CSRC, name)
+        if os.path.exists(path):
+            with open(path, "rb") as f:
+                h.update(name.encode())
+                h.update(f.read())
+    return h.hexdigest()
+
+
 def stale():
-    deps = [os.path.join(CSRC, s) for s in _sources()] + [os.path.join(CSRC, h) for h in HEADERS]
-    return _mtime(LIB_PATH) < max(_mtime(d) for d in deps)
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
+        return True
+    with open(HASH_PATH) as f:
+        return f.read().strip() != source_hash()
 
 
 def _compile(src):
@@ -68,6 +88,8 @@ def build(force=False, verbose=True):
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("link failed:\n%s\n%s" % (proc.stdout, proc.stderr))
+    with open(HASH_PATH, "w") as f:
+        f.write(source_hash())
     return LIB_PATH
 
 
