@@ -154,7 +154,9 @@ int bp_search_reset(bp_search *s);
  * the rollout kernels and in the advance kernels of the last run, over n_depths depths. */
 int bp_search_set_profiling(bp_search *s, int on);
 int bp_search_profile(bp_search *s, double *rollout_ms, double *advance_ms, int *n_depths);
-/* run every depth on the context's stream; asynchronous; single rank only */
+/* run every depth; asynchronous; single rank only.  Each shape class runs its depth loop on
+ * an internal stream forked from and joined to the context's stream with events, so the call
+ * is ordered with other work on the context's stream like a single kernel would be. */
 int bp_search_run(bp_search *s);
 /* stepwise form (root-parallel): for depth d = 0, 1, ... until bp_search_max_depth:
  *   bp_search_step_rollouts(s)      rollouts for every child of every live problem
