@@ -16,6 +16,18 @@ from ._native import Tree, pack_occupancy, pack_tiles, unpack_occupancy
 EPS = 0.1
 
 
+def _mask_and_normalise_rows(pi, valids):
+    """Row-wise form of _mask_and_normalise for a batch of leaves (same float64 operations
+    per row: multiply, sum along the row, divide)."""
+    p = np.asarray(pi, dtype=np.float64) * valids
+    total = p.sum(axis=1, keepdims=True)
+    masked = total[:, 0] <= 0
+    if masked.any():
+        p[masked] = p[masked] + valids[masked]
+        total[masked] = p[masked].sum(axis=1, keepdims=True)
+    return p / total
+
+
 def _mask_and_normalise(pi, valids):
     """Ps = Ps * valids; renormalise; uniform over valid moves when everything is masked
     (binpack/MCTS.py:281-292)."""
@@ -139,9 +151,7 @@ class BatchedMCTS(object):
                     pi, v = self.predict_batch(grids, tiles[need].astype(np.float32))
                 else:
                     pi, v = self.predict_batch(grids)
-                pi = np.asarray(pi, dtype=np.float64)
-                for k, i in enumerate(need):
-                    priors[i] = _mask_and_normalise(pi[k], valid[i].astype(np.float64))
+                priors[need] = _mask_and_normalise_rows(pi, valid[need].astype(np.float64))
                 values[need] = np.asarray(v, dtype=np.float64).reshape(-1)
                 self.leaf_evals += int(need.size)
                 self.leaf_batches += 1
