@@ -214,6 +214,17 @@ int bp_tree_set_root(bp_tree *t, const uint32_t *occ, const uint8_t *tiles);
 int bp_tree_select(bp_tree *t, uint32_t *out_leaf_occ, uint8_t *out_leaf_tiles,
                    uint8_t *out_valid, int32_t *out_status);
 int bp_tree_backup(bp_tree *t, const double *priors, const double *values, double *out_values);
+/* Device-resident form of one simulation (many trees, PyTorch net on the same stream): the
+ * leaf boards (uint32[n_trees][rows][wpr]), padded tile lists (uint8[n_trees][E][2]), valid
+ * masks (uint8[n_trees][E]) and status (int32[n_trees]) stay in device buffers owned by the
+ * tree; bp_tree_backup_dev takes the net's raw float32 policy [n_trees][E] and value
+ * [n_trees] device tensors and does the masking, normalisation and uniform fallback of
+ * MCTS.py:281-292 on the device.  No host copy, no synchronisation; bp_tree_check reports
+ * a node-pool overflow afterwards. */
+int bp_tree_select_dev(bp_tree *t, void **leaf_occ_dev, void **leaf_tiles_dev, void **valid_dev,
+                       void **status_dev);
+int bp_tree_backup_dev(bp_tree *t, const void *policy_f32_dev, const void *values_f32_dev);
+int bp_tree_check(bp_tree *t, int *overflow);
 /* counts[i][a] = Nsa[(root_i, a)]; n_nodes (nullable)[i] = nodes in tree i */
 int bp_tree_root_counts(bp_tree *t, int32_t *counts, int32_t *n_nodes);
 /* same counts left on the device (int32[n_trees][n_entries]) for an NCCL all-reduce */

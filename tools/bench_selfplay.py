@@ -17,6 +17,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--games", type=int, default=256)
     ap.add_argument("--sims", type=int, default=50)
+    ap.add_argument("--host-leaves", action="store_true", help="evaluate leaves through host copies")
     a = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -35,7 +36,8 @@ def main():
     game = BinPackGame(20, 20, 15, device=local)
     net = TorchBinPackNet(game, device="cuda:%d" % local)
     args = {"numMCTSSims": a.sims, "cpuct": 1.0, "tempThreshold": 15}
-    sp = BatchedSelfPlay(20, 20, 15, net, args, n_games=a.games, device=local, seed=rank)
+    sp = BatchedSelfPlay(20, 20, 15, net, args, n_games=a.games, device=local, seed=rank,
+                         device_leaves=not a.host_leaves)
     sp.play()                                            # warm-up (cudnn autotune, allocations)
     torch.cuda.synchronize()
     if world > 1:
@@ -67,6 +69,7 @@ def main():
     print(json.dumps({
         "config": "BinPackGame(20,20,15), numMCTSSims=%d, cpuct=1" % a.sims, "games": a.games,
         "n_gpus": world, "aggregate_searches_per_s": searches_all / dt_all,
+        "leaf_path": "host" if a.host_leaves else "device",
         "batched_searches_per_s": searches / dt, "batched_seconds": dt,
         "examples": len(examples), "mean_reward": float(reward.mean()),
         "mean_leaf_batch": evals / max(batches, 1), "leaf_batches": batches,

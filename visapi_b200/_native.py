@@ -79,6 +79,10 @@ SYMBOLS = [
     ("bp_tree_set_root", C.c_int, [_vp, _vp, _vp]),
     ("bp_tree_select", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("bp_tree_backup", C.c_int, [_vp, _vp, _vp, _vp]),
+    ("bp_tree_select_dev", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp), C.POINTER(_vp),
+                                     C.POINTER(_vp)]),
+    ("bp_tree_backup_dev", C.c_int, [_vp, _vp, _vp]),
+    ("bp_tree_check", C.c_int, [_vp, C.POINTER(C.c_int)]),
     ("bp_tree_root_counts", C.c_int, [_vp, _vp, _vp]),
     ("bp_tree_root_counts_dev", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     ("bp_tree_destroy", C.c_int, [_vp]),
@@ -464,6 +468,23 @@ class Tree(object):
         if out is None:
             self.engine.synchronize()
         return out
+
+    def select_dev(self):
+        """Device pointers (leaf occupancy, leaf tiles, valid masks, status); no sync."""
+        a, b, c, d = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.engine._check(self._lib.bp_tree_select_dev(self._h, C.byref(a), C.byref(b), C.byref(c),
+                                                        C.byref(d)))
+        return a.value, b.value, c.value, d.value
+
+    def backup_dev(self, policy_ptr, values_ptr):
+        self.engine._check(self._lib.bp_tree_backup_dev(self._h, C.c_void_p(int(policy_ptr)),
+                                                        C.c_void_p(int(values_ptr))))
+
+    def check(self):
+        flag = C.c_int()
+        self.engine._check(self._lib.bp_tree_check(self._h, C.byref(flag)))
+        if flag.value:
+            raise EngineError("a PUCT tree ran out of nodes (raise maxNodes)")
 
     def root_counts(self):
         counts = np.zeros((self.B, self.E), np.int32)

@@ -93,7 +93,8 @@ class Coach(object):
 class BatchedSelfPlay(object):
     """n_games episodes of BinPackGame(height, width, n_tiles) in lock step on one GPU."""
 
-    def __init__(self, height, width, n_tiles, nnet, args, n_games, device=None, seed=0):
+    def __init__(self, height, width, n_tiles, nnet, args, n_games, device=None, seed=0,
+                 device_leaves=True):
         self.height, self.width, self.n_tiles = height, width, n_tiles
         self.nnet, self.args, self.B = nnet, args, int(n_games)
         self.game = BinPackGame(height, width, n_tiles, device=device)
@@ -102,6 +103,8 @@ class BatchedSelfPlay(object):
         self.search = BatchedMCTS(
             height, width, 2 * n_tiles, self._predict, self.num_sims, float(_arg(args, 'cpuct', 1.0)),
             self.B, device=device, with_tiles=True)
+        # leaves evaluated without leaving the device when the net offers predict_batch_dev
+        self.device_leaves = device_leaves and hasattr(nnet, "predict_batch_dev")
         self.leaf_batches = 0
 
     def _predict(self, grids, tiles):
@@ -123,7 +126,10 @@ class BatchedSelfPlay(object):
         while not done.all():
             step += 1
             self.search.set_roots(np.stack([b[0] for b in boards]), np.stack([b[1] for b in boards]))
-            self.search.simulate()
+            if self.device_leaves:
+                self.search.simulate_on_device(self.nnet.predict_batch_dev)
+            else:
+                self.search.simulate()
             searches += self.num_sims * int((~done).sum())
             temp = int(step < int(_arg(self.args, 'tempThreshold', 15)))
             probs = self.search.action_probs(temp=temp)

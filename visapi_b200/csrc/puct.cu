@@ -306,6 +306,7 @@ tree_select_kernel(TreeParams p, uint32_t* __restrict__ out_occ, uint8_t* __rest
         p.leaf[tree] = leaf;
         p.leaf_value[tree] = value;
         out_status[tree] = status;
+        if (status < 0) *p.overflow = 1;          // reported by bp_tree_select / bp_tree_check
     }
 }
 
@@ -344,6 +345,71 @@ tree_backup_kernel(TreeParams p, const double* __restrict__ priors, const double
             p.ns[(size_t)tree * p.cap + node] += 1;
         }
         out_value[tree] = v;
+    }
+}
+
+// Device-resident leaf path: raw float32 policy [B][E] and value [B] straight from the net's
+// output tensors; masking with the valid moves, normalisation (float64) and the uniform
+// fallback of MCTS.py:281-292 happen here, then the same backup as tree_backup_kernel.
+__global__ void __launch_bounds__(TREE_WARPS * 32)
+tree_backup_dev_kernel(TreeParams p, const float* __restrict__ policy, const float* __restrict__ values)
+{
+    const int tree = blockIdx.x * TREE_WARPS + (threadIdx.x >> 5);
+    if (tree >= p.n_trees) return;
+    const int lane = lane_id();
+    const int leaf = p.leaf[tree];
+    double v = p.leaf_value[tree];
+    if (leaf >= 0) {
+        const size_t idx = (size_t)tree * p.cap + leaf;
+        const uint4 vm = p.valid[idx];
+        const uint32_t vmask[4] = {vm.x, vm.y, vm.z, vm.w};
+        double mine[4] = {0.0, 0.0, 0.0, 0.0};
+        double total = 0.0;
+        int n_valid = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = lane + 32 * j;
+            if (a < p.n_entries && ((vmask[j] >> lane) & 1u)) {
+                mine[j] = (double)policy[(size_t)tree * p.n_entries + a];
+                total += mine[j];
+                n_valid += 1;
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            total += __shfl_xor_sync(FULLMASK, total, o);
+            n_valid += __shfl_xor_sync(FULLMASK, n_valid, o);
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int a = lane + 32 * j;
+            if (a < p.n_entries) {
+                const bool ok = (vmask[j] >> lane) & 1u;
+                double pr = 0.0;
+                if (ok) pr = total > 0.0 ? mine[j] / total : 1.0 / (double)n_valid;
+                p.psa[idx * p.n_entries + a] = pr;
+            }
+        }
+        if (lane == 0) {
+            p.flags[idx] |= 2;
+            p.ns[idx] = 0;
+        }
+        v = (double)values[tree];
+    }
+    if (lane == 0) {
+        const int len = p.path_len[tree];
+        for (int i = len - 1; i >= 0; --i) {
+            const int node = p.path_node[(size_t)tree * p.max_path + i];
+            const int a = p.path_action[(size_t)tree * p.max_path + i];
+            const size_t e = ((size_t)tree * p.cap + node) * p.n_entries + a;
+            const int n = p.nsa[e];
+            if (n > 0)
+                p.qsa[e] = __ddiv_rn(__dadd_rn(__dmul_rn((double)n, p.qsa[e]), v), (double)(n + 1));
+            else
+                p.qsa[e] = v;
+            p.nsa[e] = n + 1;
+            p.ns[(size_t)tree * p.cap + node] += 1;
+        }
     }
 }
 
@@ -559,6 +625,53 @@ int bp_tree_root_counts(bp_tree* t, int32_t* counts, int32_t* n_nodes)
     if (n_nodes)
         BP_CUDA(cudaMemcpyAsync(n_nodes, p.n_nodes, (size_t)p.n_trees * 4, cudaMemcpyDeviceToHost, st));
     BP_CUDA(cudaStreamSynchronize(st));
+    return BP_OK;
+}
+
+/* device-resident simulation step: no host copies, no synchronisation */
+int bp_tree_select_dev(bp_tree* t, void** leaf_occ_dev, void** leaf_tiles_dev, void** valid_dev,
+                       void** status_dev)
+{
+    BP_REQUIRE(t && leaf_occ_dev && leaf_tiles_dev && valid_dev && status_dev, "null argument");
+    BP_CUDA(cudaSetDevice(t->ctx->device));
+    const TreeParams& p = t->p;
+    const int grid = (p.n_trees + TREE_WARPS - 1) / TREE_WARPS;
+    dispatch_class(t->cls, [&](auto R, auto Wc, auto E) {
+        tree_select_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
+            <<<grid, TREE_WARPS * 32, 0, t->ctx->stream>>>(p, t->d_leaf_occ, t->d_leaf_tiles,
+                                                            t->d_leaf_valid, t->d_status);
+    });
+    t->ctx->launches++;
+    BP_CUDA(cudaGetLastError());
+    *leaf_occ_dev = t->d_leaf_occ;
+    *leaf_tiles_dev = t->d_leaf_tiles;
+    *valid_dev = t->d_leaf_valid;
+    *status_dev = t->d_status;
+    return BP_OK;
+}
+
+int bp_tree_backup_dev(bp_tree* t, const void* policy_f32_dev, const void* values_f32_dev)
+{
+    BP_REQUIRE(t && policy_f32_dev && values_f32_dev, "null argument");
+    BP_CUDA(cudaSetDevice(t->ctx->device));
+    const TreeParams& p = t->p;
+    const int grid = (p.n_trees + TREE_WARPS - 1) / TREE_WARPS;
+    tree_backup_dev_kernel<<<grid, TREE_WARPS * 32, 0, t->ctx->stream>>>(
+        p, static_cast<const float*>(policy_f32_dev), static_cast<const float*>(values_f32_dev));
+    t->ctx->launches++;
+    BP_CUDA(cudaGetLastError());
+    return BP_OK;
+}
+
+/* 1 if any tree ran out of nodes or hit an invalid path since the last reset (synchronises) */
+int bp_tree_check(bp_tree* t, int* overflow)
+{
+    BP_REQUIRE(t && overflow, "null argument");
+    BP_CUDA(cudaSetDevice(t->ctx->device));
+    int flag = 0;
+    BP_CUDA(cudaMemcpyAsync(&flag, t->p.overflow, sizeof(int), cudaMemcpyDeviceToHost, t->ctx->stream));
+    BP_CUDA(cudaStreamSynchronize(t->ctx->stream));
+    *overflow = flag;
     return BP_OK;
 }
 

@@ -94,6 +94,16 @@ class TorchBinPackNet(NeuralNet):
             pi = torch.softmax(logits.double(), dim=1)
         return pi.cpu().numpy(), v.double().cpu().numpy()
 
+    def predict_batch_dev(self, grids, tiles):
+        """cuda tensors in (grids [B, H, W] 0/1 float32, tiles [B, 2n, 2] float32), cuda tensors
+        out (softmax policy [B, 2n] float32, value [B] float32); nothing leaves the device."""
+        torch = self.torch
+        self.model.eval()
+        with torch.no_grad():
+            logits, v = self.model(grids.reshape(-1, 1, self.height, self.width),
+                                   tiles.reshape(-1, self.n_actions, 2) / self.scale)
+            return torch.softmax(logits, dim=1), v
+
     def predict(self, board):
         if isinstance(board, tuple):
             pi, v = self.predict_batch(np.asarray(board[0])[None], np.asarray(board[1])[None])

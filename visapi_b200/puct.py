@@ -157,6 +157,34 @@ class BatchedMCTS(object):
                 self.leaf_batches += 1
             self._tree.backup(priors, values, want_values=False)
 
+    # ---- device-resident leaf path ------------------------------------------------------
+    def simulate_on_device(self, predict_dev, n=None):
+        """Same lock-step simulations with no host copy in the loop: the leaf boards stay in
+        device buffers, ``predict_dev(grids [B, H, W] float32 cuda tensor, tiles [B, 2n, 2]
+        float32 cuda tensor) -> (policy [B, 2n] float32, value [B] float32)`` runs on the same
+        CUDA stream, and masking / normalising the policy happens in the backup kernel."""
+        import torch
+        from .parallel import _DevicePointer
+        B, H, W, E = self.B, self.height, self.width, self.n_actions
+        wpr = (W + 31) // 32
+        shifts = None
+        for _ in range(self.num_sims if n is None else n):
+            occ_p, tiles_p, _valid_p, _status_p = self._tree.select_dev()
+            if shifts is None:
+                dev = torch.device("cuda", self._tree.engine.device)
+                occ_t = torch.as_tensor(_DevicePointer(occ_p, B * H * wpr * 4), device=dev)
+                occ_t = occ_t.view(torch.int32).view(B, H, wpr, 1)
+                tiles_t = torch.as_tensor(_DevicePointer(tiles_p, B * E * 2), device=dev).view(B, E, 2)
+                shifts = torch.arange(32, device=dev, dtype=torch.int32).view(1, 1, 1, 32)
+            grids = ((occ_t >> shifts) & 1).reshape(B, H, wpr * 32)[:, :, :W].to(torch.float32)
+            policy, value = predict_dev(grids, tiles_t.to(torch.float32))
+            policy = policy.to(torch.float32).contiguous()
+            value = value.to(torch.float32).contiguous()
+            self._tree.backup_dev(policy.data_ptr(), value.data_ptr())
+            self.leaf_batches += 1
+            self.leaf_evals += B
+        self._tree.check()
+
     def action_probs(self, temp=1):
         counts = self._tree.root_counts()[0].astype(np.float64)
         if temp == 0:
