@@ -59,7 +59,8 @@ class TorchBinPackNet(NeuralNet):
     """predict(board) -> (pi [2n], v) with board = (grid, tiles) or just the grid
     (binpack/MCTS.py:277 passes the grid only; then the tile tower sees zeros)."""
 
-    def __init__(self, game, device=None, lr=1e-3, epochs=5, batch_size=64, seed=0):
+    def __init__(self, game, device=None, lr=1e-3, epochs=5, batch_size=64, seed=0,
+                 inference_dtype="bfloat16"):
         import torch
         self.torch = torch
         self.height, self.width = game.getBoardSize()[0], game.getBoardSize()[1]
@@ -69,8 +70,13 @@ class TorchBinPackNet(NeuralNet):
                                    ("cuda" if torch.cuda.is_available() else "cpu"))
         torch.manual_seed(seed)
         self.model = _build_model(self.height, self.width, self.n_actions).to(self.device)
+        if self.device.type == "cuda":
+            self.model = self.model.to(memory_format=torch.channels_last)
         self.opt = torch.optim.Adam(self.model.parameters(), lr=lr)
         self.epochs, self.batch_size = epochs, batch_size
+        # leaf evaluation in self-play runs under autocast (tensor cores via cuDNN/cuBLAS); the
+        # policy softmax and the value are returned in float32
+        self.inference_dtype = getattr(torch, inference_dtype) if inference_dtype else None
 
     # ---- inference -------------------------------------------------------------------
     def _tensors(self, grids, tiles):
@@ -99,10 +105,15 @@ class TorchBinPackNet(NeuralNet):
         out (softmax policy [B, 2n] float32, value [B] float32); nothing leaves the device."""
         torch = self.torch
         self.model.eval()
+        g = grids.reshape(-1, 1, self.height, self.width).contiguous(memory_format=torch.channels_last)
+        t = tiles.reshape(-1, self.n_actions, 2) / self.scale
         with torch.no_grad():
-            logits, v = self.model(grids.reshape(-1, 1, self.height, self.width),
-                                   tiles.reshape(-1, self.n_actions, 2) / self.scale)
-            return torch.softmax(logits, dim=1), v
+            if self.inference_dtype is not None and g.is_cuda:
+                with torch.autocast("cuda", dtype=self.inference_dtype):
+                    logits, v = self.model(g, t)
+            else:
+                logits, v = self.model(g, t)
+            return torch.softmax(logits.float(), dim=1), v.float()
 
     def predict(self, board):
         if isinstance(board, tuple):
