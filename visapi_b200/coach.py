@@ -111,45 +111,61 @@ class BatchedSelfPlay(object):
         return self.nnet.predict_batch(grids, tiles)
 
     def play(self):
-        """-> (examples, rewards [B], searches) ; examples as Coach.executeEpisode makes them."""
-        boards = []
-        for _ in range(self.B):
+        """-> (examples, rewards [B], searches); examples as Coach.executeEpisode makes them:
+        (grid, tiles, pi, reward of that game).  All per-move bookkeeping is array-wise: the
+        B boards live in two numpy arrays, the move of every game is sampled in one shot, the
+        transitions and terminal tests are one batched device call each."""
+        from . import runtime
+        from ._native import PLACED, pack_occupancy, unpack_occupancy
+        eng = runtime.get_engine(self.game.device)
+        B, H, W, E = self.B, self.height, self.width, 2 * self.n_tiles
+        grids = np.zeros((B, H, W), np.uint8)
+        tiles = np.zeros((B, E, 2), np.uint8)
+        for i in range(B):
             self.game.getInitBoard()                       # a fresh random instance per game
-            boards.append((np.zeros([self.height, self.width]),
-                           np.array([[int(t[0]), int(t[1])] for t in self.game._base_board.tiles])))
+            tiles[i] = np.asarray(self.game._base_board.tiles, dtype=np.uint8)
         self.search.reset()
-        done = np.zeros(self.B, bool)
-        reward = np.zeros(self.B)
-        pending = [[] for _ in range(self.B)]
+        done = np.zeros(B, bool)
+        reward = np.zeros(B)
+        ex_game, ex_grid, ex_tiles, ex_pi = [], [], [], []
         step = 0
         searches = 0
+        temp_moves = int(_arg(self.args, 'tempThreshold', 15))
         while not done.all():
             step += 1
-            self.search.set_roots(np.stack([b[0] for b in boards]), np.stack([b[1] for b in boards]))
+            self.search.set_roots(grids, tiles)
             if self.device_leaves:
                 self.search.simulate_on_device(self.nnet.predict_batch_dev)
             else:
                 self.search.simulate()
-            searches += self.num_sims * int((~done).sum())
-            temp = int(step < int(_arg(self.args, 'tempThreshold', 15)))
-            probs = self.search.action_probs(temp=temp)
-            actions = np.zeros(self.B, np.int32)
-            for i in range(self.B):
-                if done[i]:
-                    continue
-                pending[i].append((boards[i][0].copy(), boards[i][1].copy(), probs[i].copy()))
-                actions[i] = self.rng.choice(len(probs[i]), p=probs[i])
-            live = [i for i in range(self.B) if not done[i]]
-            nxt, verdict = self.game.getNextState_batch([boards[i] for i in live], 1, actions[live])
-            for k, i in enumerate(live):
-                boards[i] = (nxt[k][0], np.asarray(nxt[k][1]))
-            ended = self.game.getGameEnded_batch([boards[i] for i in live])
-            for k, i in enumerate(live):
-                if ended[k] != 0:
-                    done[i] = True
-                    reward[i] = ended[k]
+            live = np.flatnonzero(~done)
+            searches += self.num_sims * live.size
+            probs = self.search.action_probs(temp=int(step < temp_moves))[live]
+            ex_game.append(live)
+            ex_grid.append(grids[live].astype(np.float32))
+            ex_tiles.append(tiles[live].astype(np.int64))
+            ex_pi.append(probs)
+            # one draw per live game: first action whose cumulative probability exceeds u
+            cdf = np.cumsum(probs, axis=1)
+            u = self.rng.random(live.size) * cdf[:, -1]
+            actions = np.minimum((cdf <= u[:, None]).sum(axis=1), E - 1).astype(np.int32)
+            zero = probs[np.arange(live.size), actions] <= 0       # guard against rounding at the edge
+            if zero.any():
+                actions[zero] = probs[zero].argmax(axis=1)
+            out_occ, out_tiles, verdict, _ = eng.transitions(pack_occupancy(grids[live]), W,
+                                                             tiles[live], actions, compact=True)
+            assert (verdict == PLACED).all()
+            grids[live] = unpack_occupancy(out_occ, W)
+            tiles[live] = out_tiles
+            ended = eng.game_ended(pack_occupancy(grids[live]), W, tiles[live])
+            fin = ended != 0
+            done[live[fin]] = True
+            reward[live[fin]] = ended[fin]
         self.leaf_batches = self.search.leaf_batches
-        examples = [(g, t, p, reward[i]) for i in range(self.B) for (g, t, p) in pending[i]]
+        examples = []
+        for games, g, t, p in zip(ex_game, ex_grid, ex_tiles, ex_pi):
+            for k, i in enumerate(games):
+                examples.append((g[k], t[k], p[k], reward[i]))
         return examples, reward, searches
 
 
