@@ -84,7 +84,7 @@ struct SearchParams {
     // lane-per-rollout tables of the current state of each problem (lanes.cuh)
     int use_lanes;
     uint32_t* planes;        // [P][8][4] bit-sliced column heights, inverted
-    uint32_t* groups;        // [P][ES][8] equal-entry / rotated-entry masks
+    uint32_t* pairs;         // [P][ES][4] bits of the two entries that leave when e is played
     uint2* tile;             // [P][ES] (h | w << 8, (1 << w) - 1)
     uint32_t* wmask;         // [P][129][4] entries with w <= x
     uint32_t* hmask;         // [P][129][4] entries with h <= y
@@ -164,7 +164,8 @@ fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
 // ------------------------------------------------------- lane-per-rollout kernel
 // Same tasks and the same 8-byte record as fs_rollout_kernel, but lane i plays rollout i of
 // the chunk on its own bit-sliced board (lanes.cuh): ~25x fewer warp instructions per
-// placement.  Used when every problem starts from an empty board (skyline invariant).
+// placement.  Used when every problem starts from an empty board (skyline invariant) and equal
+// tiles are adjacent in its tile list.
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
 fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
@@ -172,7 +173,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     constexpr int WROWS = 32 * W + 1, HROWS = (1 << NB) + 1, NE = 32 * EW;
     __shared__ uint32_t s_wmask[4][WROWS * EW];
     __shared__ uint32_t s_hmask[4][HROWS * EW];
-    __shared__ __align__(16) uint32_t s_groups[4][NE * 2 * EW];
+    __shared__ __align__(16) uint32_t s_pairs[4][NE * EW];
     __shared__ uint2 s_tile[4][NE];
     __shared__ uint8_t s_sel8[256 * 8];
     fill_select_table(s_sel8);
@@ -208,11 +209,10 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
                 const int y = i / EW, q = i % EW;
                 s_hmask[warp][i] = (y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
             }
-            const uint32_t* gg = p.groups + (size_t)prob * p.es * LANES_GROUP_WORDS;
-            for (int i = lane; i < NE * 2 * EW; i += 32) {
-                const int e = i / (2 * EW), q = i % (2 * EW);
-                s_groups[warp][i] = (e < d.n_entries)
-                    ? gg[e * LANES_GROUP_WORDS + (q < EW ? q : 4 + q - EW)] : 0u;
+            const uint32_t* gg = p.pairs + (size_t)prob * p.es * LANES_PAIR_WORDS;
+            for (int i = lane; i < NE * EW; i += 32) {
+                const int e = i / EW, q = i % EW;
+                s_pairs[warp][i] = (e < d.n_entries) ? gg[e * LANES_PAIR_WORDS + q] : 0u;
             }
             const uint2* gt = p.tile + (size_t)prob * p.es;
             for (int i = lane; i < NE; i += 32)
@@ -235,8 +235,8 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
 #pragma unroll
         for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)(et.x >> 8), q);
         lanes_place(s, foot, lfb.x, lfb.x + (int)(et.x & 0xFFu));
-        kill_lowest(s.alive, &s_groups[warp][entry * 2 * EW]);
-        kill_lowest(s.alive, &s_groups[warp][entry * 2 * EW + EW]);
+#pragma unroll
+        for (int q = 0; q < EW; ++q) s.alive[q] &= ~s_pairs[warp][entry * EW + q];
         const int n_alive = lfb.w - 2;
         const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
 
@@ -244,7 +244,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
         const int count = min(CHUNK, p.n_local - first);
         int my_solved;
         const int my_steps = lanes_rollout<NB, W, EW>(
-            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_groups[warp], s_tile[warp], s_sel8,
+            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_pairs[warp], s_tile[warp], s_sel8,
             p.seed, d.stream, tag,
             (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
 
@@ -311,23 +311,44 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
             gt[e] = make_uint2(s.ent[j], wdt >= 32u ? 0xFFFFFFFFu : ((1u << wdt) - 1u));
         }
     }
-    uint32_t* gg = p.groups + (size_t)prob * p.es * LANES_GROUP_WORDS;
+    uint32_t* gg = p.pairs + (size_t)prob * p.es * LANES_PAIR_WORDS;
     for (int e = 0; e < n_alive; ++e) {
         uint32_t mine = s.ent[0];
 #pragma unroll
         for (int j = 1; j < EJ; ++j) mine = ((e >> 5) == j) ? s.ent[j] : mine;
         const uint32_t v = __shfl_sync(FULLMASK, mine, e & 31);
         const uint32_t rot = ((v & 0xFFu) << 8) | (v >> 8);
-        uint32_t m[8] = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
+        // masks of the entries equal to v and to its rotation (same value in every lane)
+        uint32_t gm[4] = {0u, 0u, 0u, 0u}, rm[4] = {0u, 0u, 0u, 0u};
 #pragma unroll
         for (int j = 0; j < EJ; ++j) {
-            m[j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == v);
-            m[4 + j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == rot);
+            gm[j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == v);
+            rm[j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == rot);
         }
-        uint32_t out = m[0];
+        // rank of e inside its group; the partner has the same rank in the rotated group
+        // (a square pairs with its neighbour: rank ^ 1)
+        int rank = 0;
 #pragma unroll
-        for (int q = 1; q < 8; ++q) out = (lane == q) ? m[q] : out;
-        if (lane < 8) gg[e * LANES_GROUP_WORDS + lane] = out;
+        for (int j = 0; j < 4; ++j) {
+            const int lo = 32 * j;
+            if (e >= lo + 32) rank += __popc(gm[j]);
+            else if (e > lo) rank += __popc(gm[j] & ((1u << (e - lo)) - 1u));
+        }
+        const int want = (v == rot) ? (rank ^ 1) : rank;
+        // equal entries are adjacent (host-checked), so the rotated group is one run of bits
+        int rfirst = -1, rcount = 0;
+#pragma unroll
+        for (int j = 3; j >= 0; --j) {
+            if (rm[j]) rfirst = 32 * j + (__ffs(rm[j]) - 1);
+            rcount += __popc(rm[j]);
+        }
+        const int partner = (rfirst >= 0 && want < rcount) ? rfirst + want : -1;
+        uint32_t out = 0u;                                   // lane q holds word q of the pair mask
+        if (lane < 4) {
+            if ((e >> 5) == lane) out |= 1u << (e & 31);
+            if (partner >= 0 && (partner >> 5) == lane) out |= 1u << (partner & 31);
+            gg[e * LANES_PAIR_WORDS + lane] = out;
+        }
     }
 
     // ---- wmask[x] = entries with w <= x, hmask[y] = entries with h <= y ------------------
@@ -794,10 +815,23 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         }
     }
 
-    // lane-per-rollout kernel: needs the skyline invariant (empty initial boards);
+    // lane-per-rollout kernel: needs the skyline invariant (empty initial boards) and equal
+    // tiles adjacent in every list (true for the reference's sorted lists);
     // BP_ROLLOUT=warp forces the warp-per-board kernel
     bool lanes_ok = boards == nullptr;
     if (const char* env = getenv("BP_ROLLOUT")) lanes_ok = lanes_ok && strcmp(env, "warp") != 0;
+    for (int i = 0; i < n_problems && lanes_ok; ++i) {       // equal tiles adjacent in the list?
+        const uint8_t* t = tiles + (size_t)i * entry_stride * 2;
+        std::vector<int> closed;
+        int prev = -1;
+        for (int e = 0; e < n_entries[i]; ++e) {
+            const int v = t[2 * e] | (t[2 * e + 1] << 8);
+            if (v == 0 || v == prev) continue;
+            if (std::find(closed.begin(), closed.end(), v) != closed.end()) { lanes_ok = false; break; }
+            if (prev >= 0) closed.push_back(prev);
+            prev = v;
+        }
+    }
     p.use_lanes = lanes_ok ? 1 : 0;
 
     int rc = BP_OK;
@@ -833,7 +867,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
         if (p.use_lanes) {
             TRY(dev_alloc(s, &p.planes, P * LANES_PLANE_STRIDE));
-            TRY(dev_alloc(s, &p.groups, P * p.es * LANES_GROUP_WORDS));
+            TRY(dev_alloc(s, &p.pairs, P * p.es * LANES_PAIR_WORDS));
             TRY(dev_alloc(s, &p.tile, P * p.es));
             TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
             TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));

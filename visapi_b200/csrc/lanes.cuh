@@ -35,13 +35,19 @@ namespace bp {
 // Per-problem tables prepared once per depth by the advance kernel (write_lane_tables):
 //   planes[8][4]        bit-sliced column heights of the current board
 //   wmask[x][4], hmask[y][4]   live entries with w <= x / h <= y   (x, y = 0..128)
-//   groups[e][8]        words 0..3: live entries equal to entry e, words 4..7: live entries
-//                       equal to its rotation (any list order: groups need not be adjacent)
+//   pairs[e][4]         the two entries that leave the list when entry e is played: e itself
+//                       and its partner, the entry of the rotated tile with the same rank
+//                       inside its group of equal entries (for a square: the neighbour in its
+//                       own group).  The reference removes the FIRST equal entry and the FIRST
+//                       rotated entry (solution_checker.py:319-332); with equal entries adjacent
+//                       in the list (checked on the host) removing any member of a group leaves
+//                       the same sequence of tiles, so the rollouts are identical and the removal
+//                       is two AND-NOTs instead of two find-lowest-bit chains.
 //   tile[e]             (h | w << 8, low word of the width mask (1 << w) - 1)
 constexpr int LANES_TABLE_ROWS = 129;
 constexpr int LANES_MASK_WORDS = 4;
 constexpr int LANES_PLANE_STRIDE = 32;
-constexpr int LANES_GROUP_WORDS = 8;
+constexpr int LANES_PAIR_WORDS = 4;
 
 template <int NB, int W, int EW>
 struct LaneBoard {
@@ -79,21 +85,6 @@ __device__ __forceinline__ void fill_select_table(uint8_t* sel8)
             if ((b >> bit) & 1) sel8[b * 8 + k++] = (uint8_t)bit;
         for (; k < 8; ++k) sel8[b * 8 + k] = 0;
     }
-}
-
-// clear the lowest set bit of (alive & group); returns false if there is none
-template <int EW>
-__device__ __forceinline__ bool kill_lowest(uint32_t (&alive)[EW], const uint32_t* group)
-{
-    bool done = false;
-#pragma unroll
-    for (int q = 0; q < EW; ++q) {
-        const uint32_t m = alive[q] & group[q];
-        const uint32_t low = done ? 0u : (m & (0u - m));
-        alive[q] ^= low;
-        done = done || (m != 0u);
-    }
-    return done;
 }
 
 // raise the footprint columns from height `from` (all of them) to `to`: flip plane b under
@@ -139,13 +130,13 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
 
 // One rollout per lane, all 32 lanes of the warp in lock step (same child, sims sim0 + lane).
 // `root` is the child state (identical in every lane).  Tables live in this warp's shared
-// memory: wmask[x * EW + q], hmask[y * EW + q], groups[e * 2 * EW + ..], tile[e].
+// memory: wmask[x * EW + q], hmask[y * EW + q], pairs[e * EW + q], tile[e].
 // Returns the number of placements of this lane's rollout; solved = all tiles used.
 template <int NB, int W, int EW>
 __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, int n_alive,
                                              const uint32_t* __restrict__ wmask,
                                              const uint32_t* __restrict__ hmask,
-                                             const uint32_t* __restrict__ groups,
+                                             const uint32_t* __restrict__ pairs,
                                              const uint2* __restrict__ tile,
                                              const uint8_t* __restrict__ sel8, uint32_t seed,
                                              uint32_t stream, uint32_t tag, uint32_t sim, int active,
@@ -237,8 +228,8 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
                     }
                     lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
-                    kill_lowest(s.alive, groups + e * 2 * EW);              // MCTS.py:194
-                    kill_lowest(s.alive, groups + e * 2 * EW + EW);
+#pragma unroll
+                    for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
                     n_alive -= 2;
                     steps += 1;
                 }
