@@ -144,98 +144,101 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
 {
     int steps = 0;
     solved = 0;
-    Philox4 rnd = {0u, 0u, 0u, 0u};
-    for (int it = 0;; ++it) {
-        if ((it & 3) == 0)                                   // same iteration in every lane
-            rnd = rollout_stream_block(seed, stream, tag, sim, (uint32_t)(it >> 2));
-        if (active) {
-            if (n_alive == 0) {                              // MCTS.py:167-169
-                solved = 1;
-                active = 0;
-            } else {
-                uint32_t cand[W];
-                const int hmin = lanes_min(s, cand);
-                bool go = hmin < rows;                       // else: full board, tiles left
-                // first candidate column and the run of candidates that starts there
-                uint32_t foot[W];
-                uint32_t colbit1 = 0u;
-                int col = 0, run = 0;
-                if (W == 1) {
-                    colbit1 = cand[0] & (0u - cand[0]);
-                    const uint32_t runmask = cand[0] & ~(cand[0] + colbit1);
-                    run = __popc(runmask);
-                } else if (W == 2) {
-                    const unsigned long long c64 =
-                        (unsigned long long)cand[0] | ((unsigned long long)cand[W > 1 ? 1 : 0] << 32);
-                    const unsigned long long colbit = c64 & (0ull - c64);
-                    const unsigned long long runmask = c64 & ~(c64 + colbit);
-                    run = __popcll(runmask);
-                    col = __popcll(colbit - 1ull);
-                } else {
-                    // first non-empty word, then the run may continue through whole words
-                    bool found = false, extending = false;
-#pragma unroll
-                    for (int q = 0; q < W; ++q) {
-                        const uint32_t cq = cand[q];
-                        if (!found) {
-                            if (cq != 0u) {
-                                found = true;
-                                const uint32_t colbit = cq & (0u - cq);
-                                const uint32_t runmask = cq & ~(cq + colbit);
-                                col = 32 * q + __popc(colbit - 1u);
-                                run = __popc(runmask);
-                                extending = (runmask >> 31) != 0u;
-                            }
-                        } else if (extending) {
-                            run += __popc(cq & ~(cq + 1u));        // trailing ones
-                            extending = (cq == 0xFFFFFFFFu);
-                        }
-                    }
-                }
-                const int hidx = max(rows - hmin, 0);
-                uint32_t legal[EW];
-                int k = 0;
-#pragma unroll
-                for (int q = 0; q < EW; ++q) {
-                    legal[q] = s.alive[q] & wmask[run * EW + q] & hmask[hidx * EW + q];
-                    k += __popc(legal[q]);
-                }
-                go = go && (k != 0);                         // MCTS.py:171-172
-                if (!go) {
+    // one lock-step iteration; `u` is this lane's draw for the step
+    auto iterate = [&](uint32_t u) -> bool {
+            if (active) {
+                if (n_alive == 0) {                              // MCTS.py:167-169
+                    solved = 1;
                     active = 0;
                 } else {
-                    const uint32_t lo = (it & 1) ? rnd.y : rnd.x;
-                    const uint32_t hi = (it & 1) ? rnd.w : rnd.z;
-                    const uint32_t u = (it & 2) ? hi : lo;
-                    int idx = (int)__umulhi(u, (uint32_t)k);                // MCTS.py:174
-                    uint32_t m = legal[0];
-                    int base = 0;
-#pragma unroll
-                    for (int q = 1; q < EW; ++q) {
-                        const int cnt = __popc(legal[q - 1]);
-                        const bool past = (base == 32 * (q - 1)) && (idx >= cnt);
-                        idx -= past ? cnt : 0;
-                        m = past ? legal[q] : m;
-                        base = past ? 32 * q : base;
-                    }
-                    const int e = base + select_bit32_lut(m, idx, sel8);
-                    const uint2 t = tile[e];                                // (h | w << 8, (1 << w) - 1)
-                    const int th = (int)(t.x & 0xFFu), tw = (int)(t.x >> 8);
+                    uint32_t cand[W];
+                    const int hmin = lanes_min(s, cand);
+                    bool go = hmin < rows;                       // else: full board, tiles left
+                    // first candidate column and the run of candidates that starts there
+                    uint32_t foot[W];
+                    uint32_t colbit1 = 0u;
+                    int col = 0, run = 0;
                     if (W == 1) {
-                        foot[0] = colbit1 * t.y;                            // width mask shifted to col
+                        colbit1 = cand[0] & (0u - cand[0]);
+                        const uint32_t runmask = cand[0] & ~(cand[0] + colbit1);
+                        run = __popc(runmask);
+                    } else if (W == 2) {
+                        const unsigned long long c64 =
+                            (unsigned long long)cand[0] | ((unsigned long long)cand[W > 1 ? 1 : 0] << 32);
+                        const unsigned long long colbit = c64 & (0ull - c64);
+                        const unsigned long long runmask = c64 & ~(c64 + colbit);
+                        run = __popcll(runmask);
+                        col = __popcll(colbit - 1ull);
                     } else {
+                        // first non-empty word, then the run may continue through whole words
+                        bool found = false, extending = false;
 #pragma unroll
-                        for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
+                        for (int q = 0; q < W; ++q) {
+                            const uint32_t cq = cand[q];
+                            if (!found) {
+                                if (cq != 0u) {
+                                    found = true;
+                                    const uint32_t colbit = cq & (0u - cq);
+                                    const uint32_t runmask = cq & ~(cq + colbit);
+                                    col = 32 * q + __popc(colbit - 1u);
+                                    run = __popc(runmask);
+                                    extending = (runmask >> 31) != 0u;
+                                }
+                            } else if (extending) {
+                                run += __popc(cq & ~(cq + 1u));        // trailing ones
+                                extending = (cq == 0xFFFFFFFFu);
+                            }
+                        }
                     }
-                    lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
+                    const int hidx = max(rows - hmin, 0);
+                    uint32_t legal[EW];
+                    int k = 0;
 #pragma unroll
-                    for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
-                    n_alive -= 2;
-                    steps += 1;
+                    for (int q = 0; q < EW; ++q) {
+                        legal[q] = s.alive[q] & wmask[run * EW + q] & hmask[hidx * EW + q];
+                        k += __popc(legal[q]);
+                    }
+                    go = go && (k != 0);                         // MCTS.py:171-172
+                    if (!go) {
+                        active = 0;
+                    } else {
+                        int idx = (int)__umulhi(u, (uint32_t)k);                // MCTS.py:174
+                        uint32_t m = legal[0];
+                        int base = 0;
+#pragma unroll
+                        for (int q = 1; q < EW; ++q) {
+                            const int cnt = __popc(legal[q - 1]);
+                            const bool past = (base == 32 * (q - 1)) && (idx >= cnt);
+                            idx -= past ? cnt : 0;
+                            m = past ? legal[q] : m;
+                            base = past ? 32 * q : base;
+                        }
+                        const int e = base + select_bit32_lut(m, idx, sel8);
+                        const uint2 t = tile[e];                                // (h | w << 8, (1 << w) - 1)
+                        const int th = (int)(t.x & 0xFFu), tw = (int)(t.x >> 8);
+                        if (W == 1) {
+                            foot[0] = colbit1 * t.y;                            // width mask shifted to col
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
+                        }
+                        lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
+#pragma unroll
+                        for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
+                        n_alive -= 2;
+                        steps += 1;
+                    }
                 }
             }
-        }
-        if (!__any_sync(FULLMASK, active != 0)) break;
+        return __any_sync(FULLMASK, active != 0);
+    };
+    // four iterations per Philox block, unrolled so that the word of the block is static
+    for (uint32_t block = 0;; ++block) {
+        const Philox4 rnd = rollout_stream_block(seed, stream, tag, sim, block);
+        if (!iterate(rnd.x)) break;
+        if (!iterate(rnd.y)) break;
+        if (!iterate(rnd.z)) break;
+        if (!iterate(rnd.w)) break;
     }
     return steps;
 }
