@@ -181,16 +181,25 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
     const unsigned n_children = p.child_count[depth_slot * FS_CLASSES + cls];
+    // Work unit = `group` consecutive 32-rollout chunks of ONE child: the problem's tables (shared
+    // memory) and the child board (registers) are set up once per unit.  Units stay small
+    // when there is little work (load balance) and grow up to a whole child when there is
+    // plenty (>= 8 units per resident warp).
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
+    const unsigned long long n_warps = (unsigned long long)gridDim.x * 4ull;
+    const int group = (int)min((unsigned long long)p.n_chunks, max(1ull, n_tasks / (n_warps * 8ull)));
+    const int groups_per_child = (p.n_chunks + group - 1) / group;
+    const unsigned long long n_units = (unsigned long long)n_children * groups_per_child;
     unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
     int cached_prob = -1;
     for (;;) {
-        unsigned long long task = 0;
-        if (lane == 0) task = atomicAdd(counter, 1u);
-        task = __shfl_sync(FULLMASK, task, 0);
-        if (task >= n_tasks) break;
-        const unsigned child = (unsigned)(task / p.n_chunks);
-        const int chunk = (int)(task % p.n_chunks);
+        unsigned long long unit = 0;
+        if (lane == 0) unit = atomicAdd(counter, 1u);
+        unit = __shfl_sync(FULLMASK, unit, 0);
+        if (unit >= n_units) break;
+        const unsigned child = (unsigned)(unit / groups_per_child);
+        const int chunk_begin = (int)(unit % groups_per_child) * group;
+        const int chunk_end = min(chunk_begin + group, p.n_chunks);
         const uint32_t packed = p.child_list[cls_list_offset + child];
         const int prob = (int)(packed & 0xFFFFFFu);
         const int entry = (int)(packed >> 24);
@@ -240,27 +249,29 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
         const int n_alive = lfb.w - 2;
         const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
 
-        const int first = chunk * CHUNK;
-        const int count = min(CHUNK, p.n_local - first);
-        int my_solved;
-        const int my_steps = lanes_rollout<NB, W, EW>(
-            s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_pairs[warp], s_tile[warp], s_sel8,
-            p.seed, d.stream, tag,
-            (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
+        for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+            const int first = chunk * CHUNK;
+            const int count = min(CHUNK, p.n_local - first);
+            int my_solved;
+            const int my_steps = lanes_rollout<NB, W, EW>(
+                s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_pairs[warp], s_tile[warp], s_sel8,
+                p.seed, d.stream, tag,
+                (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
 
-        const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved != 0);
-        const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
-        const int mx = __reduce_max_sync(FULLMASK, my_steps);
-        const int sum = __reduce_add_sync(FULLMASK, my_steps);
-        const int pre = __reduce_add_sync(FULLMASK, (lane <= first_lane) ? my_steps : 0);
-        if (lane == 0) {
-            ChunkRec r;
-            r.max_steps = (uint8_t)mx;
-            r.solved_lane = (uint8_t)first_lane;
-            r.sum_steps = (uint16_t)sum;
-            r.prefix_steps = (uint16_t)pre;
-            r.n_sims = (uint16_t)count;
-            p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
+            const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved != 0);
+            const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
+            const int mx = __reduce_max_sync(FULLMASK, my_steps);
+            const int sum = __reduce_add_sync(FULLMASK, my_steps);
+            const int pre = __reduce_add_sync(FULLMASK, (lane <= first_lane) ? my_steps : 0);
+            if (lane == 0) {
+                ChunkRec r;
+                r.max_steps = (uint8_t)mx;
+                r.solved_lane = (uint8_t)first_lane;
+                r.sum_steps = (uint16_t)sum;
+                r.prefix_steps = (uint16_t)pre;
+                r.n_sims = (uint16_t)count;
+                p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
+            }
         }
     }
 }
