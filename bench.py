@@ -63,8 +63,11 @@ def model_lane_inst_per_placement(key):
 
 
 # raw ncu thread instructions / placement and DRAM bytes / launch of that kernel (profiles/r1/)
-MEASURED_LANE_THREAD_INST = {"5,1,2": 196.4, "5,2,2": 255.7, "6,1,2": 205.9, "6,2,2": 267.5}
-MEASURED_LANE_DRAM_BYTES_PER_LAUNCH = 216647.0
+# (ncu_lanes5_inst_*.csv: 150 problems per class, N=960; 120 launches, launch-weighted mean)
+MEASURED_LANE_THREAD_INST = {"5,1,2": 161.0, "5,2,2": 206.8, "6,1,2": 171.8, "6,2,2": 234.8}
+MEASURED_LANE_DRAM_BYTES_PER_LAUNCH = 166819.0
+# ncu --set full of fs_rollout_lanes_kernel<5,1,2> (ncu_full_fs_rollout_lanes_5_1_2.csv)
+MEASURED_LANE_PIPE_PCT = {"issue_active": 75.0, "alu": 76.6, "fma": 21.8, "xu": 28.1, "lsu": 12.4}
 
 
 def lane_class_key(rows, cols, n_entries):
@@ -364,6 +367,7 @@ def our_arm(a):
                        ("MEASURED_PEAKS.json" if "sm_max_mhz" in peaks else "nvidia-smi"),
         "measured_issue_gwarp_inst_s": {"lop3_iadd3_alu_pipe_only": alu_only,
                                         "lop3_imad_alu_plus_fma": alu_fma},
+        "ncu_pipe_pct_of_peak": MEASURED_LANE_PIPE_PCT if lane_kernel else None,
         "model": ("thread instructions per placement / 32 (lane-per-rollout)" if lane_kernel
                   else "warp instructions per placement (warp-per-board)"),
         "rollout_kernel_ms_per_step": rollout_ms, "advance_kernel_ms_per_step": advance_ms,
