@@ -63,16 +63,28 @@ __device__ __forceinline__ uint32_t word_range(int lo, int hi, int q)
 }
 
 // Position of the k-th (0-based) set bit of m, k < popc(m), through a 2 KB shared-memory
-// table: sel8[b * 8 + k] = position of the k-th set bit of byte b.  Three independent
-// popcounts (XU pipe) pick the byte and one LDS (LSU pipe) finishes: fewer ALU-pipe
-// instructions than a five-level binary select, and the ALU pipe is what binds the kernel.
+// table: sel8[b * 8 + j] = position of the j-th set bit of byte b.  The kernel is bound by the
+// ALU pipe (LOP3 / SEL / ISETP / SHF issue at half rate), so the byte search avoids it:
+//   c0..c2  = popcounts of the low 1, 2, 3 bytes (shifts as IMAD.SHL on the FMA pipe, POPC on XU)
+//   a       = 0x808080 + (k-c0) + (k-c1) << 8 + (k-c2) << 16   (four IMADs; every byte stays in
+//             [96, 159], so there is no borrow between bytes): bit 7 of byte j  <=>  k >= c_j
+//   byte    = popc(a & 0x808080)            -- the byte of m that holds the bit
+//   a2      = a << 8 | 0x80 + k             -- byte j = 0x80 + k - (popcount below byte j)
+// and two byte permutes (PRMT) pull byte `byte` out of m and of a2: 3 ALU-pipe instructions
+// instead of the 17 of a compare/select chain.
 __device__ __forceinline__ int select_bit32_lut(uint32_t m, int k, const uint8_t* __restrict__ sel8)
 {
-    const int c0 = __popc(m & 0xFFu), c1 = __popc(m & 0xFFFFu), c2 = __popc(m & 0xFFFFFFu);
-    const int byte = (k >= c0) + (k >= c1) + (k >= c2);
-    const int pre = (k >= c2) ? c2 : ((k >= c1) ? c1 : ((k >= c0) ? c0 : 0));
-    const uint32_t b = (m >> (8 * byte)) & 0xFFu;
-    return 8 * byte + (int)sel8[b * 8 + (k - pre)];
+    const uint32_t c0 = __popc(m << 24), c1 = __popc(m << 16), c2 = __popc(m << 8);
+    uint32_t a = (uint32_t)k * 0x010101u + 0x808080u;
+    a -= c0;
+    a -= c1 * 256u;
+    a -= c2 * 65536u;
+    const uint32_t byte = __popc(a & 0x808080u);
+    const uint32_t a2 = a * 256u + (0x80u + (uint32_t)k);
+    const uint32_t sel = byte + 0x4440u;                 // result byte 0 = source byte, rest 0
+    const uint32_t bits = __byte_perm(m, 0u, sel);
+    const uint32_t rank = __byte_perm(a2, 0u, sel);      // 0x80 + rank inside the byte
+    return (int)(8u * byte) + (int)sel8[bits * 8u + rank - 0x80u];
 }
 
 // fill sel8[256 * 8] (call with all threads of the block, then __syncthreads)
@@ -113,17 +125,39 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
 {
 #pragma unroll
     for (int q = 0; q < W; ++q) cand[q] = 0xFFFFFFFFu;
+    // Per plane: one LOP3 with predicate output on the ALU pipe (the binding pipe); the
+    // conditional narrowing and the height bit are predicated multiply-adds, which issue on
+    // the FMA pipe (`one` is opaque to ptxas so they are not folded back into SEL / IADD3).
     int hmin = 0;
+    const uint32_t one = blockDim.x >> 7;         // 1 (128-thread blocks), not a constant to ptxas
 #pragma unroll
     for (int b = NB - 1; b >= 0; --b) {
-        uint32_t z[W];
-        uint32_t any = 0u;
+        if (W == 1) {
+            asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
+                "and.b32 t, %0, %2;\n\t"
+                "setp.ne.u32 p, t, 0;\n\t"
+                "@p mad.lo.u32 %0, t, %3, 0;\n\t"
+                "@!p mad.lo.u32 %1, %3, %5, %1;\n\t}"
+                : "+r"(cand[0]), "+r"(hmin) : "r"(s.pl[b][0]), "r"(one), "n"(0), "r"(1u << b));
+        } else {
+            // any = OR of the narrowed words; word 0 is narrowed by a predicated FMA-pipe move,
+            // the other words by one predicated AND each
+            uint32_t z0 = cand[0] & s.pl[b][0];
+            uint32_t any = z0;
 #pragma unroll
-        for (int q = 0; q < W; ++q) { z[q] = cand[q] & s.pl[b][q]; any |= z[q]; }
-        const bool has_zero = any != 0u;          // some candidate has bit b of its height clear
+            for (int q = 1; q < W; ++q) any |= cand[q] & s.pl[b][q];
+            asm("{\n\t.reg .pred p;\n\t"
+                "setp.ne.u32 p, %3, 0;\n\t"
+                "@p mad.lo.u32 %0, %2, %4, 0;\n\t"
+                "@!p mad.lo.u32 %1, %4, %5, %1;\n\t}"
+                : "+r"(cand[0]), "+r"(hmin) : "r"(z0), "r"(any), "r"(one), "r"(1u << b));
 #pragma unroll
-        for (int q = 0; q < W; ++q) cand[q] = has_zero ? z[q] : cand[q];
-        hmin |= has_zero ? 0 : (1 << b);
+            for (int q = 1; q < W; ++q)
+                asm("{\n\t.reg .pred p;\n\t"
+                    "setp.ne.u32 p, %2, 0;\n\t"
+                    "@p and.b32 %0, %0, %1;\n\t}"
+                    : "+r"(cand[q]) : "r"(s.pl[b][q]), "r"(any));
+        }
     }
     return hmin;
 }
