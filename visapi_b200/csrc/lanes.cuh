@@ -49,6 +49,11 @@ constexpr int LANES_MASK_WORDS = 4;
 constexpr int LANES_PLANE_STRIDE = 32;
 constexpr int LANES_PAIR_WORDS = 4;
 
+// The value 1, read from constant memory so that ptxas cannot fold it: `x * FMA_ONE + y` stays an
+// IMAD (FMA pipe) where a plain move / add / select would be scheduled on the ALU pipe that
+// binds this kernel (LOP3, SEL, ISETP, SHF issue at half rate on sm_100).
+static __constant__ uint32_t FMA_ONE = 1u;
+
 template <int NB, int W, int EW>
 struct LaneBoard {
     uint32_t pl[NB][W];    // bit-sliced column heights, stored INVERTED (bit set = height bit clear)
@@ -72,19 +77,23 @@ __device__ __forceinline__ uint32_t word_range(int lo, int hi, int q)
 //   a2      = a << 8 | 0x80 + k             -- byte j = 0x80 + k - (popcount below byte j)
 // and two byte permutes (PRMT) pull byte `byte` out of m and of a2: 3 ALU-pipe instructions
 // instead of the 17 of a compare/select chain.
-__device__ __forceinline__ int select_bit32_lut(uint32_t m, int k, const uint8_t* __restrict__ sel8)
+// `kp` = 0x80 + k, `base` is added to the result.
+__device__ __forceinline__ int select_bit32_lut(uint32_t m, uint32_t kp, uint32_t base,
+                                                const uint8_t* __restrict__ sel8)
 {
     const uint32_t c0 = __popc(m << 24), c1 = __popc(m << 16), c2 = __popc(m << 8);
-    uint32_t a = (uint32_t)k * 0x010101u + 0x808080u;
+    uint32_t a = kp * 0x010101u;
     a -= c0;
     a -= c1 * 256u;
     a -= c2 * 65536u;
     const uint32_t byte = __popc(a & 0x808080u);
-    const uint32_t a2 = a * 256u + (0x80u + (uint32_t)k);
-    const uint32_t sel = byte + 0x4440u;                 // result byte 0 = source byte, rest 0
-    const uint32_t bits = __byte_perm(m, 0u, sel);
-    const uint32_t rank = __byte_perm(a2, 0u, sel);      // 0x80 + rank inside the byte
-    return (int)(8u * byte) + (int)sel8[bits * 8u + rank - 0x80u];
+    const uint32_t a2 = a * 256u + kp;
+    uint32_t sel;                                        // result byte 0 = source byte, rest 0
+    asm("mad.lo.u32 %0, %1, %2, 0x4440;" : "=r"(sel) : "r"(byte), "r"(FMA_ONE));
+    uint32_t bits, rank;                                 // rank = 0x80 + rank inside the byte
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(bits) : "r"(m), "r"(sel));
+    asm("prmt.b32 %0, %1, 0, %2;" : "=r"(rank) : "r"(a2), "r"(sel));
+    return (int)(8u * byte + base) + (int)sel8[bits * 8u + rank - 0x80u];
 }
 
 // fill sel8[256 * 8] (call with all threads of the block, then __syncthreads)
@@ -129,7 +138,7 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
     // conditional narrowing and the height bit are predicated multiply-adds, which issue on
     // the FMA pipe (`one` is opaque to ptxas so they are not folded back into SEL / IADD3).
     int hmin = 0;
-    const uint32_t one = blockDim.x >> 7;         // 1 (128-thread blocks), not a constant to ptxas
+    const uint32_t one = FMA_ONE;
 #pragma unroll
     for (int b = NB - 1; b >= 0; --b) {
         if (W == 1) {
@@ -178,16 +187,16 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
 {
     int steps = 0;
     solved = 0;
+    if (active && n_alive == 0) {                                // MCTS.py:167-169: nothing to place
+        solved = 1;
+        active = 0;
+    }
     // one lock-step iteration; `u` is this lane's draw for the step
     auto iterate = [&](uint32_t u) -> bool {
             if (active) {
-                if (n_alive == 0) {                              // MCTS.py:167-169
-                    solved = 1;
-                    active = 0;
-                } else {
+                {
                     uint32_t cand[W];
                     const int hmin = lanes_min(s, cand);
-                    bool go = hmin < rows;                       // else: full board, tiles left
                     // first candidate column and the run of candidates that starts there
                     uint32_t foot[W];
                     uint32_t colbit1 = 0u;
@@ -225,29 +234,43 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         }
                     }
                     const int hidx = max(rows - hmin, 0);
-                    uint32_t legal[EW];
+                    uint32_t legal[EW], cnt[EW];
                     int k = 0;
 #pragma unroll
                     for (int q = 0; q < EW; ++q) {
                         legal[q] = s.alive[q] & wmask[run * EW + q] & hmask[hidx * EW + q];
-                        k += __popc(legal[q]);
+                        cnt[q] = (uint32_t)__popc(legal[q]);
+                        k += (int)cnt[q];
                     }
-                    go = go && (k != 0);                         // MCTS.py:171-172
-                    if (!go) {
+                    // MCTS.py:171-172; a full board with tiles left has hidx = 0 and hmask[0] = 0
+                    if (k == 0) {
                         active = 0;
                     } else {
-                        int idx = (int)__umulhi(u, (uint32_t)k);                // MCTS.py:174
-                        uint32_t m = legal[0];
-                        int base = 0;
+                        const uint32_t idx = __umulhi(u, (uint32_t)k);          // MCTS.py:174
+                        // word of the legal mask that holds the idx-th entry; kp = 0x80 + rank
+                        // inside that word.  Predicated FMA-pipe moves instead of selects.
+                        uint32_t kp, m = legal[0], base = 0u;
+                        asm("mad.lo.u32 %0, %1, %2, 0x80;" : "=r"(kp) : "r"(idx), "r"(FMA_ONE));
+                        if (EW == 2) {
+                            asm("{\n\t.reg .pred p;\n\t"
+                                "setp.ge.u32 p, %3, %4;\n\t"
+                                "@p mad.lo.u32 %0, %5, %6, 0;\n\t"
+                                "@p sub.u32 %1, %1, %4;\n\t"
+                                "@p mad.lo.u32 %2, %6, 32, 0;\n\t}"
+                                : "+r"(m), "+r"(kp), "+r"(base)
+                                : "r"(idx), "r"(cnt[0]), "r"(legal[EW > 1 ? 1 : 0]), "r"(FMA_ONE));
+                        } else {
+                            uint32_t rem = idx;
 #pragma unroll
-                        for (int q = 1; q < EW; ++q) {
-                            const int cnt = __popc(legal[q - 1]);
-                            const bool past = (base == 32 * (q - 1)) && (idx >= cnt);
-                            idx -= past ? cnt : 0;
-                            m = past ? legal[q] : m;
-                            base = past ? 32 * q : base;
+                            for (int q = 1; q < EW; ++q) {
+                                const bool past = (base == 32u * (q - 1)) && (rem >= cnt[q - 1]);
+                                rem -= past ? cnt[q - 1] : 0u;
+                                kp -= past ? cnt[q - 1] : 0u;
+                                m = past ? legal[q] : m;
+                                base = past ? 32u * q : base;
+                            }
                         }
-                        const int e = base + select_bit32_lut(m, idx, sel8);
+                        const int e = select_bit32_lut(m, kp, base, sel8);
                         const uint2 t = tile[e];                                // (h | w << 8, (1 << w) - 1)
                         const int th = (int)(t.x & 0xFFu), tw = (int)(t.x >> 8);
                         if (W == 1) {
@@ -261,6 +284,10 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
                         n_alive -= 2;
                         steps += 1;
+                        if (n_alive == 0) {                      // MCTS.py:167-169 of the next step
+                            solved = 1;
+                            active = 0;
+                        }
                     }
                 }
             }
