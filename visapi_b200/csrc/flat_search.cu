@@ -85,7 +85,7 @@ struct SearchParams {
     int use_lanes;
     uint32_t* planes;        // [P][8][4] bit-sliced column heights, inverted
     uint32_t* pairs;         // [P][ES][4] bits of the two entries that leave when e is played
-    uint2* tile;             // [P][ES] (h | w << 8, (1 << w) - 1)
+    uint4* tile;             // [P][ES] (h, w, width mask (1 << w) - 1 as lo / hi word)
     uint32_t* wmask;         // [P][129][4] entries with w <= x
     uint32_t* hmask;         // [P][129][4] entries with h <= y
 };
@@ -174,7 +174,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     __shared__ uint32_t s_wmask[4][WROWS * EW];
     __shared__ uint32_t s_hmask[4][HROWS * EW];
     __shared__ __align__(16) uint32_t s_pairs[4][NE * EW];
-    __shared__ uint2 s_tile[4][NE];
+    __shared__ __align__(16) typename LaneTile<W>::type s_tile[4][NE];
     __shared__ uint8_t s_sel8[256 * 8];
     fill_select_table(s_sel8);
     __syncthreads();
@@ -223,9 +223,9 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
                 const int e = i / EW, q = i % EW;
                 s_pairs[warp][i] = (e < d.n_entries) ? gg[e * LANES_PAIR_WORDS + q] : 0u;
             }
-            const uint2* gt = p.tile + (size_t)prob * p.es;
+            const uint4* gt = p.tile + (size_t)prob * p.es;
             for (int i = lane; i < NE; i += 32)
-                s_tile[warp][i] = (i < d.n_entries) ? gt[i] : make_uint2(0u, 0u);
+                s_tile[warp][i] = LaneTile<W>::pack((i < d.n_entries) ? gt[i] : make_uint4(0u, 0u, 0u, 0u));
             __syncwarp();
             cached_prob = prob;
         }
@@ -239,11 +239,11 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
             for (int q = 0; q < W; ++q) s.pl[b][q] = gp[b * 4 + q];
 #pragma unroll
         for (int q = 0; q < EW; ++q) s.alive[q] = word_range(0, lfb.w, q);
-        const uint2 et = s_tile[warp][entry];
+        const uint4 et = p.tile[(size_t)prob * p.es + entry];
         uint32_t foot[W];
 #pragma unroll
-        for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)(et.x >> 8), q);
-        lanes_place(s, foot, lfb.x, lfb.x + (int)(et.x & 0xFFu));
+        for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)et.y, q);
+        lanes_place(s, foot, lfb.x, lfb.x + (int)et.x);
 #pragma unroll
         for (int q = 0; q < EW; ++q) s.alive[q] &= ~s_pairs[warp][entry * EW + q];
         const int n_alive = lfb.w - 2;
@@ -313,13 +313,14 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
             if (lane == b * 4 + q) gp[lane] = (q < W) ? ~pl[b][q < W ? q : 0] : 0u;   // inverted
 
     // ---- per-entry tile record and the masks of equal / rotated live entries -------------
-    uint2* gt = p.tile + (size_t)prob * p.es;
+    uint4* gt = p.tile + (size_t)prob * p.es;
 #pragma unroll
     for (int j = 0; j < EJ; ++j) {
         const int e = lane + 32 * j;
         if (e < d.n_entries) {
             const uint32_t wdt = s.ent[j] >> 8;
-            gt[e] = make_uint2(s.ent[j], wdt >= 32u ? 0xFFFFFFFFu : ((1u << wdt) - 1u));
+            const unsigned long long wm = wdt >= 64u ? ~0ull : ((1ull << wdt) - 1ull);
+            gt[e] = make_uint4(s.ent[j] & 0xFFu, wdt, (uint32_t)wm, (uint32_t)(wm >> 32));
         }
     }
     uint32_t* gg = p.pairs + (size_t)prob * p.es * LANES_PAIR_WORDS;

@@ -43,7 +43,8 @@ namespace bp {
 //                       in the list (checked on the host) removing any member of a group leaves
 //                       the same sequence of tiles, so the rollouts are identical and the removal
 //                       is two AND-NOTs instead of two find-lowest-bit chains.
-//   tile[e]             (h | w << 8, low word of the width mask (1 << w) - 1)
+//   tile[e]             (h, w, width mask (1 << w) - 1 as two words); in shared memory (h, mask)
+//                       for one-word boards and all four words otherwise
 constexpr int LANES_TABLE_ROWS = 129;
 constexpr int LANES_MASK_WORDS = 4;
 constexpr int LANES_PLANE_STRIDE = 32;
@@ -53,6 +54,18 @@ constexpr int LANES_PAIR_WORDS = 4;
 // IMAD (FMA pipe) where a plain move / add / select would be scheduled on the ALU pipe that
 // binds this kernel (LOP3, SEL, ISETP, SHF issue at half rate on sm_100).
 static __constant__ uint32_t FMA_ONE = 1u;
+
+// shared-memory tile record of a W-word board
+template <int W>
+struct LaneTile {
+    typedef uint4 type;
+    static __device__ __forceinline__ uint4 pack(uint4 t) { return t; }
+};
+template <>
+struct LaneTile<1> {
+    typedef uint2 type;
+    static __device__ __forceinline__ uint2 pack(uint4 t) { return make_uint2(t.x, t.z); }
+};
 
 template <int NB, int W, int EW>
 struct LaneBoard {
@@ -107,6 +120,10 @@ __device__ __forceinline__ void fill_select_table(uint8_t* sel8)
         for (; k < 8; ++k) sel8[b * 8 + k] = 0;
     }
 }
+
+// word i of a tile record (z / w exist only in the four-word record)
+__device__ __forceinline__ uint32_t tile_word(const uint4& t, int i) { return i == 2 ? t.z : t.w; }
+__device__ __forceinline__ uint32_t tile_word(const uint2&, int) { return 0u; }
 
 // raise the footprint columns from height `from` (all of them) to `to`: flip plane b under
 // the footprint wherever bit b differs (a flip is the same on inverted planes)
@@ -180,7 +197,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                                              const uint32_t* __restrict__ wmask,
                                              const uint32_t* __restrict__ hmask,
                                              const uint32_t* __restrict__ pairs,
-                                             const uint2* __restrict__ tile,
+                                             const typename LaneTile<W>::type* __restrict__ tile,
                                              const uint8_t* __restrict__ sel8, uint32_t seed,
                                              uint32_t stream, uint32_t tag, uint32_t sim, int active,
                                              int& solved)
@@ -200,6 +217,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                     // first candidate column and the run of candidates that starts there
                     uint32_t foot[W];
                     uint32_t colbit1 = 0u;
+                    unsigned long long colbit64 = 0ull;
                     int col = 0, run = 0;
                     if (W == 1) {
                         colbit1 = cand[0] & (0u - cand[0]);
@@ -208,10 +226,9 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                     } else if (W == 2) {
                         const unsigned long long c64 =
                             (unsigned long long)cand[0] | ((unsigned long long)cand[W > 1 ? 1 : 0] << 32);
-                        const unsigned long long colbit = c64 & (0ull - c64);
-                        const unsigned long long runmask = c64 & ~(c64 + colbit);
+                        colbit64 = c64 & (0ull - c64);
+                        const unsigned long long runmask = c64 & ~(c64 + colbit64);
                         run = __popcll(runmask);
-                        col = __popcll(colbit - 1ull);
                     } else {
                         // first non-empty word, then the run may continue through whole words
                         bool found = false, extending = false;
@@ -271,11 +288,19 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                             }
                         }
                         const int e = select_bit32_lut(m, kp, base, sel8);
-                        const uint2 t = tile[e];                                // (h | w << 8, (1 << w) - 1)
-                        const int th = (int)(t.x & 0xFFu), tw = (int)(t.x >> 8);
+                        const typename LaneTile<W>::type t = tile[e];
+                        const int th = (int)t.x;
                         if (W == 1) {
-                            foot[0] = colbit1 * t.y;                            // width mask shifted to col
+                            foot[0] = colbit1 * t.y;                 // width mask shifted to col
+                        } else if (W == 2) {
+                            // 64-bit product colbit * width mask: three IMADs, no shifts
+                            const unsigned long long f =
+                                colbit64 * ((unsigned long long)tile_word(t, 2) |
+                                            ((unsigned long long)tile_word(t, 3) << 32));
+                            foot[0] = (uint32_t)f;
+                            foot[W > 1 ? 1 : 0] = (uint32_t)(f >> 32);
                         } else {
+                            const int tw = (int)t.y;
 #pragma unroll
                             for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
                         }
