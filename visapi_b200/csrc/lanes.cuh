@@ -166,23 +166,22 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
                 "@!p mad.lo.u32 %1, %3, %5, %1;\n\t}"
                 : "+r"(cand[0]), "+r"(hmin) : "r"(s.pl[b][0]), "r"(one), "n"(0), "r"(1u << b));
         } else {
-            // any = OR of the narrowed words; word 0 is narrowed by a predicated FMA-pipe move,
-            // the other words by one predicated AND each
-            uint32_t z0 = cand[0] & s.pl[b][0];
-            uint32_t any = z0;
+            // any = OR of the narrowed words; each word is replaced by a predicated FMA-pipe move
+            uint32_t z[W];
+            uint32_t any = 0u;
 #pragma unroll
-            for (int q = 1; q < W; ++q) any |= cand[q] & s.pl[b][q];
+            for (int q = 0; q < W; ++q) { z[q] = cand[q] & s.pl[b][q]; any |= z[q]; }
             asm("{\n\t.reg .pred p;\n\t"
                 "setp.ne.u32 p, %3, 0;\n\t"
                 "@p mad.lo.u32 %0, %2, %4, 0;\n\t"
                 "@!p mad.lo.u32 %1, %4, %5, %1;\n\t}"
-                : "+r"(cand[0]), "+r"(hmin) : "r"(z0), "r"(any), "r"(one), "r"(1u << b));
+                : "+r"(cand[0]), "+r"(hmin) : "r"(z[0]), "r"(any), "r"(one), "r"(1u << b));
 #pragma unroll
             for (int q = 1; q < W; ++q)
                 asm("{\n\t.reg .pred p;\n\t"
                     "setp.ne.u32 p, %2, 0;\n\t"
-                    "@p and.b32 %0, %0, %1;\n\t}"
-                    : "+r"(cand[q]) : "r"(s.pl[b][q]), "r"(any));
+                    "@p mad.lo.u32 %0, %1, %3, 0;\n\t}"
+                    : "+r"(cand[q]) : "r"(z[q]), "r"(any), "r"(one));
         }
     }
     return hmin;
@@ -202,12 +201,11 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                                              uint32_t stream, uint32_t tag, uint32_t sim, int active,
                                              int& solved)
 {
-    int steps = 0;
-    solved = 0;
-    if (active && n_alive == 0) {                                // MCTS.py:167-169: nothing to place
-        solved = 1;
-        active = 0;
-    }
+    // Every placement removes two entries, so the step count and the verdict follow from the
+    // number of live entries left: no counters in the loop.
+    const int n_alive0 = n_alive;
+    const int playing = active;
+    if (n_alive == 0) active = 0;                                // MCTS.py:167-169: nothing to place
     // one lock-step iteration; `u` is this lane's draw for the step
     auto iterate = [&](uint32_t u) -> bool {
             if (active) {
@@ -308,11 +306,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
 #pragma unroll
                         for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
                         n_alive -= 2;
-                        steps += 1;
-                        if (n_alive == 0) {                      // MCTS.py:167-169 of the next step
-                            solved = 1;
-                            active = 0;
-                        }
+                        if (n_alive == 0) active = 0;            // MCTS.py:167-169 of the next step
                     }
                 }
             }
@@ -326,7 +320,8 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
         if (!iterate(rnd.z)) break;
         if (!iterate(rnd.w)) break;
     }
-    return steps;
+    solved = (playing && n_alive == 0) ? 1 : 0;
+    return (n_alive0 - n_alive) >> 1;
 }
 
 }  // namespace bp
