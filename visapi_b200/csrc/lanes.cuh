@@ -207,8 +207,12 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
     const int playing = active;
     if (n_alive == 0) active = 0;                                // MCTS.py:167-169: nothing to place
     // one lock-step iteration; `u` is this lane's draw for the step
+    // The body is branch-free: a lane whose rollout is over keeps stepping a dead state in lock
+    // step (the warp would issue the instructions for the other lanes anyway) and only its
+    // live-entry count is frozen.  With no legal entry the select reads a fixed in-range entry
+    // (legal mask 0, idx 0), so every table address stays valid.
     auto iterate = [&](uint32_t u) -> bool {
-            if (active) {
+            {
                 {
                     uint32_t cand[W];
                     const int hmin = lanes_min(s, cand);
@@ -258,9 +262,8 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         k += (int)cnt[q];
                     }
                     // MCTS.py:171-172; a full board with tiles left has hidx = 0 and hmask[0] = 0
-                    if (k == 0) {
-                        active = 0;
-                    } else {
+                    active = (k != 0) ? active : 0;
+                    {
                         const uint32_t idx = __umulhi(u, (uint32_t)k);          // MCTS.py:174
                         // word of the legal mask that holds the idx-th entry; kp = 0x80 + rank
                         // inside that word.  Predicated FMA-pipe moves instead of selects.
@@ -305,7 +308,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
 #pragma unroll
                         for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
-                        n_alive -= 2;
+                        n_alive -= active ? 2 : 0;
                         if (n_alive == 0) active = 0;            // MCTS.py:167-169 of the next step
                     }
                 }
