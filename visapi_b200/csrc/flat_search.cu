@@ -173,8 +173,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     constexpr int WROWS = 32 * W + 1, HROWS = (1 << NB) + 1, NE = 32 * EW;
     __shared__ uint32_t s_wmask[4][WROWS * EW];
     __shared__ uint32_t s_hmask[4][HROWS * EW];
-    __shared__ __align__(16) uint32_t s_pairs[4][NE * EW];
-    __shared__ __align__(16) typename LaneTile<W>::type s_tile[4][NE];
+    __shared__ LaneEntry<W, EW> s_entries[4][NE];
     __shared__ uint8_t s_sel8[256 * 8];
     fill_select_table(s_sel8);
     __syncthreads();
@@ -218,14 +217,14 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
                 const int y = i / EW, q = i % EW;
                 s_hmask[warp][i] = (y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
             }
-            const uint32_t* gg = p.pairs + (size_t)prob * p.es * LANES_PAIR_WORDS;
-            for (int i = lane; i < NE * EW; i += 32) {
-                const int e = i / EW, q = i % EW;
-                s_pairs[warp][i] = (e < d.n_entries) ? gg[e * LANES_PAIR_WORDS + q] : 0u;
-            }
+            const uint4* gg = reinterpret_cast<const uint4*>(p.pairs) + (size_t)prob * p.es;
             const uint4* gt = p.tile + (size_t)prob * p.es;
-            for (int i = lane; i < NE; i += 32)
-                s_tile[warp][i] = LaneTile<W>::pack((i < d.n_entries) ? gt[i] : make_uint4(0u, 0u, 0u, 0u));
+            for (int i = lane; i < NE; i += 32) {
+                const bool in = i < d.n_entries;
+                const uint4 pr = in ? gg[i] : make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t pair[4] = {pr.x, pr.y, pr.z, pr.w};
+                s_entries[warp][i].set(in ? gt[i] : make_uint4(0u, 0u, 0u, 0u), pair);
+            }
             __syncwarp();
             cached_prob = prob;
         }
@@ -245,7 +244,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
         for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)et.y, q);
         lanes_place(s, foot, lfb.x, lfb.x + (int)et.x);
 #pragma unroll
-        for (int q = 0; q < EW; ++q) s.alive[q] &= ~s_pairs[warp][entry * EW + q];
+        for (int q = 0; q < EW; ++q) s.alive[q] &= ~s_entries[warp][entry].pair(q);
         const int n_alive = lfb.w - 2;
         const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
 
@@ -254,7 +253,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
             const int count = min(CHUNK, p.n_local - first);
             int my_solved;
             const int my_steps = lanes_rollout<NB, W, EW>(
-                s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_pairs[warp], s_tile[warp], s_sel8,
+                s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_entries[warp], s_sel8,
                 p.seed, d.stream, tag,
                 (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
 

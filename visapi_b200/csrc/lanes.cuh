@@ -55,16 +55,37 @@ constexpr int LANES_PAIR_WORDS = 4;
 // binds this kernel (LOP3, SEL, ISETP, SHF issue at half rate on sm_100).
 static __constant__ uint32_t FMA_ONE = 1u;
 
-// shared-memory tile record of a W-word board
-template <int W>
-struct LaneTile {
-    typedef uint4 type;
-    static __device__ __forceinline__ uint4 pack(uint4 t) { return t; }
+// Shared-memory record of one entry: its tile and its pair mask behind ONE address, so a step
+// computes one table address and issues one or two vector loads.  Built from the global
+// tile record (h, w, width mask lo, hi) and the entry's pair-mask words.
+template <int W, int EW>
+struct __align__(16) LaneEntry {                  // 32 bytes
+    uint4 t;                                      // h, w, width mask lo / hi
+    uint32_t pr[4];                               // pair mask
+    __device__ __forceinline__ void set(const uint4& tile, const uint32_t (&pair)[4])
+    {
+        t = tile;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) pr[q] = pair[q];
+    }
+    __device__ __forceinline__ uint32_t h() const { return t.x; }
+    __device__ __forceinline__ uint32_t w() const { return t.y; }
+    __device__ __forceinline__ uint32_t wm_lo() const { return t.z; }
+    __device__ __forceinline__ uint32_t wm_hi() const { return t.w; }
+    __device__ __forceinline__ uint32_t pair(int q) const { return pr[q]; }
 };
 template <>
-struct LaneTile<1> {
-    typedef uint2 type;
-    static __device__ __forceinline__ uint2 pack(uint4 t) { return make_uint2(t.x, t.z); }
+struct __align__(16) LaneEntry<1, 2> {            // 16 bytes: one-word board, <= 64 entries
+    uint4 v;                                      // h, width mask, pair mask lo / hi
+    __device__ __forceinline__ void set(const uint4& tile, const uint32_t (&pair)[4])
+    {
+        v = make_uint4(tile.x, tile.z, pair[0], pair[1]);
+    }
+    __device__ __forceinline__ uint32_t h() const { return v.x; }
+    __device__ __forceinline__ uint32_t w() const { return 0u; }
+    __device__ __forceinline__ uint32_t wm_lo() const { return v.y; }
+    __device__ __forceinline__ uint32_t wm_hi() const { return 0u; }
+    __device__ __forceinline__ uint32_t pair(int q) const { return q == 0 ? v.z : v.w; }
 };
 
 template <int NB, int W, int EW>
@@ -120,10 +141,6 @@ __device__ __forceinline__ void fill_select_table(uint8_t* sel8)
         for (; k < 8; ++k) sel8[b * 8 + k] = 0;
     }
 }
-
-// word i of a tile record (z / w exist only in the four-word record)
-__device__ __forceinline__ uint32_t tile_word(const uint4& t, int i) { return i == 2 ? t.z : t.w; }
-__device__ __forceinline__ uint32_t tile_word(const uint2&, int) { return 0u; }
 
 // raise the footprint columns from height `from` (all of them) to `to`: flip plane b under
 // the footprint wherever bit b differs (a flip is the same on inverted planes)
@@ -189,14 +206,13 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
 
 // One rollout per lane, all 32 lanes of the warp in lock step (same child, sims sim0 + lane).
 // `root` is the child state (identical in every lane).  Tables live in this warp's shared
-// memory: wmask[x * EW + q], hmask[y * EW + q], pairs[e * EW + q], tile[e].
+// memory: wmask[x * EW + q], hmask[y * EW + q], entries[e].
 // Returns the number of placements of this lane's rollout; solved = all tiles used.
 template <int NB, int W, int EW>
 __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, int n_alive,
                                              const uint32_t* __restrict__ wmask,
                                              const uint32_t* __restrict__ hmask,
-                                             const uint32_t* __restrict__ pairs,
-                                             const typename LaneTile<W>::type* __restrict__ tile,
+                                             const LaneEntry<W, EW>* __restrict__ entries,
                                              const uint8_t* __restrict__ sel8, uint32_t seed,
                                              uint32_t stream, uint32_t tag, uint32_t sim, int active,
                                              int& solved)
@@ -261,8 +277,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         cnt[q] = (uint32_t)__popc(legal[q]);
                         k += (int)cnt[q];
                     }
-                    // MCTS.py:171-172; a full board with tiles left has hidx = 0 and hmask[0] = 0
-                    active = (k != 0) ? active : 0;
+                                    active = min(active, k);                     // 0 / 1 flag; k == 0: MCTS.py:171-172
                     {
                         const uint32_t idx = __umulhi(u, (uint32_t)k);          // MCTS.py:174
                         // word of the legal mask that holds the idx-th entry; kp = 0x80 + rank
@@ -289,27 +304,27 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                             }
                         }
                         const int e = select_bit32_lut(m, kp, base, sel8);
-                        const typename LaneTile<W>::type t = tile[e];
-                        const int th = (int)t.x;
+                        const LaneEntry<W, EW> t = entries[e];
+                        const int th = (int)t.h();
                         if (W == 1) {
-                            foot[0] = colbit1 * t.y;                 // width mask shifted to col
+                            foot[0] = colbit1 * t.wm_lo();           // width mask shifted to col
                         } else if (W == 2) {
                             // 64-bit product colbit * width mask: three IMADs, no shifts
                             const unsigned long long f =
-                                colbit64 * ((unsigned long long)tile_word(t, 2) |
-                                            ((unsigned long long)tile_word(t, 3) << 32));
+                                colbit64 * ((unsigned long long)t.wm_lo() |
+                                            ((unsigned long long)t.wm_hi() << 32));
                             foot[0] = (uint32_t)f;
                             foot[W > 1 ? 1 : 0] = (uint32_t)(f >> 32);
                         } else {
-                            const int tw = (int)t.y;
+                            const int tw = (int)t.w();
 #pragma unroll
                             for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
                         }
                         lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
 #pragma unroll
-                        for (int q = 0; q < EW; ++q) s.alive[q] &= ~pairs[e * EW + q];   // MCTS.py:194
-                        n_alive -= active ? 2 : 0;
-                        if (n_alive == 0) active = 0;            // MCTS.py:167-169 of the next step
+                        for (int q = 0; q < EW; ++q) s.alive[q] &= ~t.pair(q);       // MCTS.py:194
+                        n_alive -= 2 * active;
+                        active = min(active, n_alive);           // MCTS.py:167-169 of the next step
                     }
                 }
             }
