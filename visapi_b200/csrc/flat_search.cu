@@ -213,9 +213,10 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
                 const int x = i / EW, q = i % EW;
                 s_wmask[warp][i] = (x <= d.cols) ? gw[x * LANES_MASK_WORDS + q] : 0u;
             }
+            // row inv of the shared table = entries with h <= rows - hmin, hmin = 2^NB - 1 - inv
             for (int i = lane; i < HROWS * EW; i += 32) {
-                const int y = i / EW, q = i % EW;
-                s_hmask[warp][i] = (y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
+                const int y = i / EW - ((1 << NB) - 1 - d.rows), q = i % EW;
+                s_hmask[warp][i] = (y >= 0 && y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
             }
             const uint4* gg = reinterpret_cast<const uint4*>(p.pairs) + (size_t)prob * p.es;
             const uint4* gt = p.tile + (size_t)prob * p.es;

@@ -162,26 +162,33 @@ __device__ __forceinline__ void lanes_place(LaneBoard<NB, W, EW>& s, const uint3
     }
 }
 
-// leftmost column of minimum height: cand = columns of minimum height, hmin = that height
+// Leftmost column of minimum height: cand = columns of minimum height; returns that height in
+// the planes' own inverted form, inv = (2^NB - 1) - hmin, which is what the callers need (the
+// hmask rows are laid out by inv, and a placement flips the bits where inv and inv - h differ).
+// Per plane: one LOP3 with predicate output on the ALU pipe (the binding pipe); the
+// conditional narrowing and the height bit are predicated multiply-adds, which issue on the
+// FMA pipe (FMA_ONE is opaque to ptxas so they are not folded back into SEL / IADD3).
 template <int NB, int W, int EW>
 __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t (&cand)[W])
 {
-#pragma unroll
-    for (int q = 0; q < W; ++q) cand[q] = 0xFFFFFFFFu;
-    // Per plane: one LOP3 with predicate output on the ALU pipe (the binding pipe); the
-    // conditional narrowing and the height bit are predicated multiply-adds, which issue on
-    // the FMA pipe (`one` is opaque to ptxas so they are not folded back into SEL / IADD3).
-    int hmin = 0;
     const uint32_t one = FMA_ONE;
+    // top plane: every column is still a candidate
+    uint32_t top = 0u;
 #pragma unroll
-    for (int b = NB - 1; b >= 0; --b) {
+    for (int q = 0; q < W; ++q) top |= s.pl[NB - 1][q];
+    const bool top_set = top != 0u;
+#pragma unroll
+    for (int q = 0; q < W; ++q) cand[q] = top_set ? s.pl[NB - 1][q] : 0xFFFFFFFFu;
+    int inv = top_set ? (1 << (NB - 1)) : 0;
+#pragma unroll
+    for (int b = NB - 2; b >= 0; --b) {
         if (W == 1) {
             asm("{\n\t.reg .pred p;\n\t.reg .b32 t;\n\t"
                 "and.b32 t, %0, %2;\n\t"
                 "setp.ne.u32 p, t, 0;\n\t"
                 "@p mad.lo.u32 %0, t, %3, 0;\n\t"
-                "@!p mad.lo.u32 %1, %3, %5, %1;\n\t}"
-                : "+r"(cand[0]), "+r"(hmin) : "r"(s.pl[b][0]), "r"(one), "n"(0), "r"(1u << b));
+                "@p mad.lo.u32 %1, %3, %4, %1;\n\t}"
+                : "+r"(cand[0]), "+r"(inv) : "r"(s.pl[b][0]), "r"(one), "r"(1u << b));
         } else {
             // any = OR of the narrowed words; each word is replaced by a predicated FMA-pipe move
             uint32_t z[W];
@@ -191,8 +198,8 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
             asm("{\n\t.reg .pred p;\n\t"
                 "setp.ne.u32 p, %3, 0;\n\t"
                 "@p mad.lo.u32 %0, %2, %4, 0;\n\t"
-                "@!p mad.lo.u32 %1, %4, %5, %1;\n\t}"
-                : "+r"(cand[0]), "+r"(hmin) : "r"(z[0]), "r"(any), "r"(one), "r"(1u << b));
+                "@p mad.lo.u32 %1, %4, %5, %1;\n\t}"
+                : "+r"(cand[0]), "+r"(inv) : "r"(z[0]), "r"(any), "r"(one), "r"(1u << b));
 #pragma unroll
             for (int q = 1; q < W; ++q)
                 asm("{\n\t.reg .pred p;\n\t"
@@ -201,12 +208,13 @@ __device__ __forceinline__ int lanes_min(const LaneBoard<NB, W, EW>& s, uint32_t
                     : "+r"(cand[q]) : "r"(z[q]), "r"(any), "r"(one));
         }
     }
-    return hmin;
+    return inv;
 }
 
 // One rollout per lane, all 32 lanes of the warp in lock step (same child, sims sim0 + lane).
 // `root` is the child state (identical in every lane).  Tables live in this warp's shared
-// memory: wmask[x * EW + q], hmask[y * EW + q], entries[e].
+// memory: wmask[x * EW + q], hmask[inv * EW + q] (row inv = entries that fit above a column of
+// inverted height inv), entries[e].
 // Returns the number of placements of this lane's rollout; solved = all tiles used.
 template <int NB, int W, int EW>
 __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, int n_alive,
@@ -227,11 +235,11 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
     // step (the warp would issue the instructions for the other lanes anyway) and only its
     // live-entry count is frozen.  With no legal entry the select reads a fixed in-range entry
     // (legal mask 0, idx 0), so every table address stays valid.
-    auto iterate = [&](uint32_t u) -> bool {
+    auto iterate = [&](uint32_t u) {
             {
                 {
                     uint32_t cand[W];
-                    const int hmin = lanes_min(s, cand);
+                    const int inv = lanes_min(s, cand);          // (2^NB - 1) - minimum height
                     // first candidate column and the run of candidates that starts there
                     uint32_t foot[W];
                     uint32_t colbit1 = 0u;
@@ -268,12 +276,11 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                             }
                         }
                     }
-                    const int hidx = max(rows - hmin, 0);
                     uint32_t legal[EW], cnt[EW];
                     int k = 0;
 #pragma unroll
                     for (int q = 0; q < EW; ++q) {
-                        legal[q] = s.alive[q] & wmask[run * EW + q] & hmask[hidx * EW + q];
+                        legal[q] = s.alive[q] & wmask[run * EW + q] & hmask[inv * EW + q];
                         cnt[q] = (uint32_t)__popc(legal[q]);
                         k += (int)cnt[q];
                     }
@@ -320,7 +327,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
 #pragma unroll
                             for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
                         }
-                        lanes_place(s, foot, hmin, hmin + th);                  // MCTS.py:175-178
+                        lanes_place(s, foot, inv, inv - th);                    // MCTS.py:175-178
 #pragma unroll
                         for (int q = 0; q < EW; ++q) s.alive[q] &= ~t.pair(q);       // MCTS.py:194
                         n_alive -= 2 * active;
@@ -328,15 +335,16 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                     }
                 }
             }
-        return __any_sync(FULLMASK, active != 0);
     };
     // four iterations per Philox block, unrolled so that the word of the block is static
     for (uint32_t block = 0;; ++block) {
         const Philox4 rnd = rollout_stream_block(seed, stream, tag, sim, block);
-        if (!iterate(rnd.x)) break;
-        if (!iterate(rnd.y)) break;
-        if (!iterate(rnd.z)) break;
-        if (!iterate(rnd.w)) break;
+        iterate(rnd.x);
+        iterate(rnd.y);
+        if (!__any_sync(FULLMASK, active != 0)) break;   // (an extra step on dead lanes is harmless)
+        iterate(rnd.z);
+        iterate(rnd.w);
+        if (!__any_sync(FULLMASK, active != 0)) break;
     }
     solved = (playing && n_alive == 0) ? 1 : 0;
     return (n_alive0 - n_alive) >> 1;
