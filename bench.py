@@ -63,11 +63,13 @@ def model_lane_inst_per_placement(key):
 
 
 # raw ncu thread instructions / placement and DRAM bytes / launch of that kernel (profiles/r1/)
-# (ncu_lanes5_inst_*.csv: 150 problems per class, N=960; 120 launches, launch-weighted mean)
-MEASURED_LANE_THREAD_INST = {"5,1,2": 161.0, "5,2,2": 206.8, "6,1,2": 171.8, "6,2,2": 234.8}
-MEASURED_LANE_DRAM_BYTES_PER_LAUNCH = 166819.0
+# (ncu_lanes7_inst_*.csv: 150 problems per class, N=960; 120 launches, launch-weighted mean).
+# Warp instructions: the loop body is branch-free, so finished lanes ride along and thread
+# counts no longer say how many lanes do useful work.
+MEASURED_LANE_WARP_INST = {"5,1,2": 4.55, "5,2,2": 5.89, "6,1,2": 4.90, "6,2,2": 6.59}
+MEASURED_LANE_DRAM_BYTES_PER_LAUNCH = 179512.0
 # ncu --set full of fs_rollout_lanes_kernel<5,1,2> (ncu_full_fs_rollout_lanes_5_1_2.csv)
-MEASURED_LANE_PIPE_PCT = {"issue_active": 75.0, "alu": 76.6, "fma": 21.8, "xu": 28.1, "lsu": 12.4}
+MEASURED_LANE_PIPE_PCT = {"issue_active": 76.7, "alu": 66.1, "fma_heavy": 66.4, "xu": 47.8, "lsu": 15.1}
 
 
 def lane_class_key(rows, cols, n_entries):
@@ -377,7 +379,7 @@ def our_arm(a):
         "placements_executed_per_step": float(res_p["placements_executed"].sum()),
         "placements_per_s_kernel": float(res_p["placements_executed"].sum()) / (rollout_ms / 1e3),
         "algorithmic_inst_per_placement": {k: per_placement(k) for k in by_class},
-        "ncu_inst_per_placement": ({k: MEASURED_LANE_THREAD_INST.get(k, 0) / 32.0 for k in by_class}
+        "ncu_inst_per_placement": ({k: MEASURED_LANE_WARP_INST.get(k) for k in by_class}
                                    if lane_kernel else
                                    {k: MEASURED_INST_PER_PLACEMENT_V1.get(k) for k in by_class}),
         "hbm": {"algorithmic_gbs": algo_bytes / (rollout_ms / 1e3) / 1e9, "peak_gbs": hbm_peak,
