@@ -93,6 +93,9 @@ def parse_args():
                     help="seconds of the python-port CPU sample (0 = skip cpu_baseline)")
     ap.add_argument("--ref-budget", type=float, default=10.0,
                     help="--impl reference: seconds per step")
+    ap.add_argument("--mode", default="auto", choices=["auto", "stepped", "resident"],
+                    help="stepped: one rollout + one advance launch per depth and class; "
+                         "resident: one launch per shape class runs every depth; auto: stepped")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-strong", action="store_true")
     ap.add_argument("--no-verify", action="store_true")
@@ -264,6 +267,7 @@ def our_arm(a):
     search = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], a.n_sim,
                         strat, a.seed, streams)
 
+    search.set_mode(a.mode)
     flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)    # > 126 MB of L2
 
     def step():
@@ -326,6 +330,7 @@ def our_arm(a):
     search.set_profiling(True)
     step()
     rollout_ms, advance_ms, n_depths = search.profile()
+    resident = search.last_run_resident()
     res_p = search.results()
     search.set_profiling(False)
     lane_kernel = search.info()["lane_kernel"]
@@ -352,14 +357,15 @@ def our_arm(a):
     issue_peak = info["sm_count"] * 4 * sm_max_mhz * 1e6
     achieved = algo_inst / (rollout_ms / 1e3)
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-    n_launches = n_depths * search.info()["n_classes"]
+    n_launches = n_depths if resident else n_depths * search.info()["n_classes"]
     alu_only, alu_fma = eng.issue_microbench()
     # HBM bytes a rollout task needs: its problem's tables (on a problem switch) + 8 B record
     n_tasks = float(res_p["rollouts_executed"].sum()) / 32.0
     algo_bytes = n_tasks * (128 + 8) + float(res_p["depth"].sum() + P) * 2400.0
     roofline = {
         "bound": "issue",
-        "kernel": "fs_rollout_lanes_kernel" if lane_kernel else "fs_rollout_kernel",
+        "kernel": ("fs_search_resident_kernel" if resident else
+                   ("fs_rollout_lanes_kernel" if lane_kernel else "fs_rollout_kernel")),
         "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
         "frac": achieved / issue_peak,
         "traffic": MEASURED_LANE_DRAM_BYTES_PER_LAUNCH if lane_kernel else 98560.0,
@@ -374,7 +380,8 @@ def our_arm(a):
                   else "warp instructions per placement (warp-per-board)"),
         "rollout_kernel_ms_per_step": rollout_ms, "advance_kernel_ms_per_step": advance_ms,
         "rollout_kernel_share_of_step": rollout_ms / (rollout_ms + advance_ms),
-        "launches_per_step": {"rollout": n_launches, "advance": n_launches},
+        "launches_per_step": ({"resident": n_launches, "advance_first": search.info()["n_classes"]}
+                              if resident else {"rollout": n_launches, "advance": n_launches}),
         "avg_rollout_launch_ms": rollout_ms / max(n_launches, 1),
         "placements_executed_per_step": float(res_p["placements_executed"].sum()),
         "placements_per_s_kernel": float(res_p["placements_executed"].sum()) / (rollout_ms / 1e3),

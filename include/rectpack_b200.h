@@ -149,14 +149,30 @@ int bp_search_create(bp_context *ctx, int n_problems, const int32_t *rows, const
 int bp_search_set_partition(bp_search *s, int rank, int n_ranks, int sim_begin, int n_local);
 /* (re)load the initial states into HBM; must precede bp_search_run */
 int bp_search_reset(bp_search *s);
-/* on != 0: bracket every depth's rollout and advance launches with CUDA events on the
- * context's stream.  bp_search_profile synchronises and returns the milliseconds spent in
- * the rollout kernels and in the advance kernels of the last run, over n_depths depths. */
+/* How bp_search_run plays the search (results are identical either way):
+ *   BP_SEARCH_STEPPED   one rollout launch + one advance launch per depth and shape class, each
+ *                       class's depth loop on its own stream (the form the stepwise API uses);
+ *   BP_SEARCH_RESIDENT  ONE launch per shape class runs every depth of every problem: persistent
+ *                       warps take work units from a device queue, and the warp that finishes a
+ *                       problem's last rollout of a depth scores its children, commits the best
+ *                       one (CustomMCTS.predict, binpack/MCTS.py:95-119) and queues the next
+ *                       depth's rollouts, so problems advance independently.  Needs the lane
+ *                       kernel (see bp_search_info);
+ *   BP_SEARCH_AUTO      the faster of the two as measured on B200: STEPPED.
+ * The environment variable BP_SEARCH=stepped|resident overrides the mode. */
+typedef enum { BP_SEARCH_AUTO = 0, BP_SEARCH_STEPPED = 1, BP_SEARCH_RESIDENT = 2 } bp_search_mode;
+int bp_search_set_mode(bp_search *s, int mode);
+/* on != 0: time the launches of the next run with CUDA events on the context's stream, shape
+ * classes serialised.  bp_search_profile synchronises and returns, for the last run,
+ *   stepped:  milliseconds in the rollout kernels / in the advance kernels, over n_depths depths;
+ *   resident: milliseconds in the resident kernels (rollout_ms; advance_ms = 0), n_depths = the
+ *             number of launches (one per class). */
 int bp_search_set_profiling(bp_search *s, int on);
 int bp_search_profile(bp_search *s, double *rollout_ms, double *advance_ms, int *n_depths);
-/* run every depth; asynchronous; single rank only.  Each shape class runs its depth loop on
- * an internal stream forked from and joined to the context's stream with events, so the call
- * is ordered with other work on the context's stream like a single kernel would be. */
+/* run every depth; asynchronous; single rank only.  Each shape class runs on an internal
+ * stream forked from and joined to the context's stream with events, so the call is ordered
+ * with other work on the context's stream like a single kernel would be.  bp_search_results
+ * fails with BP_ERR_STATE if a resident kernel gave up (its watchdog fired). */
 int bp_search_run(bp_search *s);
 /* stepwise form (root-parallel): for depth d = 0, 1, ... until bp_search_max_depth:
  *   bp_search_step_rollouts(s)      rollouts for every child of every live problem
@@ -173,6 +189,12 @@ int bp_search_max_depth(bp_search *s, int *max_depth);
  * the environment variable BP_ROLLOUT=warp).  n_classes = shape classes in the batch, each
  * with its own launch sequence. */
 int bp_search_info(bp_search *s, int *lane_kernel, int *n_classes);
+/* resident = 1 when the last bp_search_run used the resident kernel */
+int bp_search_last_run(bp_search *s, int *resident);
+/* Where the warps of the last resident run spent their time; synchronises.  out8 = SM clock
+ * cycles summed over all warps: {resident, waiting for a unit, playing units, advancing
+ * problems}, then {units played, problems advanced, tickets taken, units published}. */
+int bp_search_resident_stats(bp_search *s, double *out8);
 /* synchronises the stream and copies results to the host
  *   results      : bp_search_result[n_problems]
  *   order        : NULL or uint8[n_problems][entry_stride / 2 + 2][2]  solution_tiles_order

@@ -41,14 +41,18 @@ SHAPES = [
 def _run_both_kernels(eng, rows, cols, tiles, n_sim, strategy, stream, boards=None):
     from visapi_b200 import pack_tiles
     out = []
-    for impl in ("lanes", "warp"):
+    # lane kernel with one launch pair per depth (the default), lane kernel inside the resident
+    # search kernel, warp-per-board kernel
+    for impl, mode in (("lanes", "stepped"), ("lanes", "resident"), ("warp", "stepped")):
         os.environ["BP_ROLLOUT"] = impl
+        os.environ["BP_SEARCH"] = mode
         try:
             out.append(eng.flat_search([rows], [cols], pack_tiles([tiles], len(tiles) + len(tiles) % 2),
                                        [len(tiles)], n_sim, strategy, 7, [stream], boards=boards,
                                        want_scores=True))
         finally:
             os.environ.pop("BP_ROLLOUT", None)
+            os.environ.pop("BP_SEARCH", None)
     return out
 
 

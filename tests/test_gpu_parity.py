@@ -302,14 +302,48 @@ def test_search_reset_is_repeatable(eng, golden):
                    c["n_sim"], 0, 123, [c["stream"]])
     s.set_profiling(True)
     outs = []
-    for _ in range(3):
-        s.reset()
-        s.run()
-        outs.append(s.results(want_scores=True))
-    rollout_ms, advance_ms, depths = s.profile()
-    assert depths == s.max_depth and rollout_ms > 0 and advance_ms > 0
+    for mode in ("stepped", "resident"):
+        s.set_mode(mode)
+        for _ in range(3):
+            s.reset()
+            s.run()
+            outs.append(s.results(want_scores=True))
+        rollout_ms, advance_ms, launches = s.profile()
+        if mode == "stepped":
+            assert not s.last_run_resident()
+            assert launches == s.max_depth and rollout_ms > 0 and advance_ms > 0
+        else:
+            assert s.last_run_resident()
+            assert launches == 1 and rollout_ms > 0 and advance_ms == 0
     for o in outs:
         _check_flat(c, o, 0, c["n_sim"], c["strategy"])
+    s.close()
+
+
+@pytest.mark.parametrize("set_name,strategy,n_sim", [("g", 0, 100), ("b", 1, 37), ("g", 1, 1000)])
+def test_resident_search_equals_stepped(eng, set_name, strategy, n_sim):
+    """The single-launch resident search (problems advance independently, the warp that finishes
+    a depth commits it) returns exactly what the launch-per-depth search returns: every field,
+    every child score, for a mixed-class batch."""
+    from visapi_b200 import datasets
+    probs = datasets.load_problem_set(set_name)[:300]
+    batch = datasets.batch_arrays(probs)
+    s = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim, strategy, 123)
+    assert s.info()["lane_kernel"]
+    ref = None
+    for mode in ("stepped", "resident", "resident"):
+        s.set_mode(mode)
+        s.reset()
+        s.run()
+        res = s.results(want_scores=True)
+        assert s.last_run_resident() == (mode == "resident")
+        if ref is None:
+            ref = res
+        for k in ("depth", "solution_found", "score", "n_order", "n_tiles_placed", "rollouts",
+                  "rollout_placements", "rollouts_executed", "placements_executed", "order", "path",
+                  "child_scores"):
+            np.testing.assert_array_equal(res[k], ref[k], err_msg="%s (%s)" % (k, mode))
+    assert int(ref["depth"].sum()) > 0
     s.close()
 
 

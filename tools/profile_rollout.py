@@ -40,6 +40,7 @@ def main():
     ap.add_argument("--n-sim", type=int, default=1000)
     ap.add_argument("--strategy", default="max_depth")
     ap.add_argument("--steps", type=int, default=1)
+    ap.add_argument("--mode", default="auto", choices=["auto", "stepped", "resident"])
     a = ap.parse_args()
     from visapi_b200 import Engine, datasets
     probs = datasets.load_problem_set(a.set)
@@ -52,6 +53,7 @@ def main():
     eng = Engine(0)
     s = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], a.n_sim,
                    0 if a.strategy == "max_depth" else 1, 123, np.arange(len(probs), dtype=np.uint32))
+    s.set_mode(a.mode)
     s.set_profiling(True)
     for _ in range(a.steps):
         s.reset()
@@ -62,7 +64,7 @@ def main():
                       "placements_executed": int(r["placements_executed"].sum()),
                       "rollouts_executed": int(r["rollouts_executed"].sum()),
                       "rollouts": int(r["rollouts"].sum()), "solved": int(r["solution_found"].sum()),
-                      "rollout_ms": rollout_ms, "advance_ms": advance_ms, "depths": n_depths}))
+                      "mode": a.mode, "resident": s.last_run_resident(), "rollout_ms": rollout_ms, "advance_ms": advance_ms, "depths": n_depths}))
 
 
 if __name__ == "__main__":

@@ -59,6 +59,7 @@ SYMBOLS = [
                                    C.c_int, _u32, C.POINTER(_vp)]),
     ("bp_search_set_partition", C.c_int, [_vp, C.c_int, C.c_int, C.c_int, C.c_int]),
     ("bp_search_reset", C.c_int, [_vp]),
+    ("bp_search_set_mode", C.c_int, [_vp, C.c_int]),
     ("bp_search_set_profiling", C.c_int, [_vp, C.c_int]),
     ("bp_search_profile", C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_double),
                                     C.POINTER(C.c_int)]),
@@ -69,6 +70,8 @@ SYMBOLS = [
     ("bp_search_stats_buffer", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     ("bp_search_max_depth", C.c_int, [_vp, C.POINTER(C.c_int)]),
     ("bp_search_info", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("bp_search_last_run", C.c_int, [_vp, C.POINTER(C.c_int)]),
+    ("bp_search_resident_stats", C.c_int, [_vp, C.POINTER(C.c_double)]),
     ("bp_search_results", C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     ("bp_search_destroy", C.c_int, [_vp]),
     ("bp_flat_search", C.c_int, [_vp, C.c_int, _vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int,
@@ -377,6 +380,27 @@ class Search(object):
 
     def run(self):
         self.engine._check(self._lib.bp_search_run(self._h))
+
+    def set_mode(self, mode):
+        """"stepped" (one launch pair per depth and class), "resident" (one launch per class runs
+        every depth) or "auto" (the faster one as measured: stepped)."""
+        self.engine._check(self._lib.bp_search_set_mode(
+            self._h, {"auto": 0, "stepped": 1, "resident": 2}[mode]))
+
+    def last_run_resident(self):
+        r = C.c_int()
+        self.engine._check(self._lib.bp_search_last_run(self._h, C.byref(r)))
+        return bool(r.value)
+
+    def resident_stats(self):
+        """Time split of the warps of the last resident run (see bp_search_resident_stats)."""
+        out = (C.c_double * 8)()
+        self.engine._check(self._lib.bp_search_resident_stats(self._h, out))
+        tot = max(out[0], 1.0)
+        return {"warp_cycles": out[0], "wait_frac": out[1] / tot, "play_frac": out[2] / tot,
+                "advance_frac": out[3] / tot, "other_frac": (out[0] - out[1] - out[2] - out[3]) / tot,
+                "units_played": int(out[4]), "advances": int(out[5]), "tickets": int(out[6]),
+                "units_published": int(out[7])}
 
     def set_profiling(self, on=True):
         self.engine._check(self._lib.bp_search_set_profiling(self._h, int(bool(on))))

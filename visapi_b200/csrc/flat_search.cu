@@ -88,7 +88,88 @@ struct SearchParams {
     uint4* tile;             // [P][ES] (h, w, width mask (1 << w) - 1 as lo / hi word)
     uint32_t* wmask;         // [P][129][4] entries with w <= x
     uint32_t* hmask;         // [P][129][4] entries with h <= y
+    // resident (single-launch) search: units of the current depth of each problem still running
+    int* pending;            // [P]
+    int res_flags;           // debugging knobs (BP_RESIDENT_FLAGS): 1 = single-chunk units, 2 = never leave
 };
+
+// ---- work queue of the resident search kernel (one per search class) -------------------
+// A unit = `chunk_count` consecutive 32-rollout chunks of one child.  Producers (the warp that
+// advances a problem) reserve a ticket range with one atomicAdd on `tail`, write the payloads,
+// fence, then write each slot's `seq` = ticket + 1.  Consumers take a ticket from `head` and
+// wait for their slot's seq.  The ring holds every unit that can be outstanding at once.
+struct UnitQueue {
+    // every hot word on its own 128-byte line: the ticket counters take one atomic per unit,
+    // the flags are polled by waiting warps
+    unsigned long long head;     // tickets handed to consumers
+    unsigned pad_h[30];
+    unsigned long long tail;     // tickets reserved by producers
+    unsigned pad_t[30];
+    int in_flight;               // problems of this class still searching
+    int abort;                   // != 0: a warp gave up waiting (watchdog) or saw a torn slot
+    int est_units;               // decaying average of units per published problem-depth
+    unsigned pad_f[29];
+    unsigned init_next;          // prologue: next problem whose depth-0 units are to be published
+    unsigned init_done;          // prologue: problems published
+    unsigned cap_mask;           // ring capacity - 1
+    unsigned pad_i[29];
+    // where the warps' time went (SM clock cycles summed over warps, added when a warp leaves)
+    unsigned long long cyc_total, cyc_wait, cyc_play, cyc_advance, n_units_played, n_advances;
+    unsigned pad_c[20];
+};
+static_assert(sizeof(UnitQueue) == 640, "queue header layout");
+struct __align__(16) UnitSlot {
+    uint32_t seq;                // (uint32_t)(ticket + 1) once the payload is valid
+    uint32_t child;              // problem | entry << 24
+    uint32_t chunk_begin, chunk_count;
+};
+constexpr int MAX_UNITS_PER_CHILD = 256;
+
+// loads of state another warp of the SAME launch may have written: through L2 (ld.global.cg),
+// never from this SM's L1
+template <bool CG, typename T>
+__device__ __forceinline__ T ld_state(const T* ptr)
+{
+    if (CG) return __ldcg(ptr);
+    return *ptr;
+}
+template <typename T>
+__device__ __forceinline__ T ld_volatile(const T* ptr) { return *reinterpret_cast<const volatile T*>(ptr); }
+template <typename T>
+__device__ __forceinline__ void st_volatile(T* ptr, T v) { *reinterpret_cast<volatile T*>(ptr) = v; }
+
+template <bool CG, int RHO, int W, int EJ>
+__device__ __forceinline__ void load_board_t(WarpState<RHO, W, EJ>& s, const uint32_t* occ, int rows,
+                                             int cols, int wpr)
+{
+    const int lane = lane_id();
+#pragma unroll
+    for (int k = 0; k < RHO; ++k) {
+        const int row = lane + 32 * k;
+#pragma unroll
+        for (int q = 0; q < W; ++q) {
+            uint32_t v = FULLMASK;
+            if (row < rows && q < wpr) {
+                v = ld_state<CG>(occ + row * wpr + q);
+                const int live = cols - 32 * q;
+                if (live < 32) v |= (live <= 0) ? FULLMASK : (FULLMASK << live);
+            }
+            s.occ[k][q] = v;
+        }
+    }
+}
+
+template <bool CG, int RHO, int W, int EJ>
+__device__ __forceinline__ void load_entries_t(WarpState<RHO, W, EJ>& s, const uint8_t* tiles, int n_entries)
+{
+    const int lane = lane_id();
+    const uint16_t* t16 = reinterpret_cast<const uint16_t*>(tiles);
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) {
+        const int e = lane + 32 * j;
+        s.ent[j] = (e < n_entries) ? (uint32_t)ld_state<CG>(t16 + e) : 0u;
+    }
+}
 
 __device__ __forceinline__ long long warp_sum_ll(long long v)
 {
@@ -166,14 +247,106 @@ fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
 // the chunk on its own bit-sliced board (lanes.cuh): ~25x fewer warp instructions per
 // placement.  Used when every problem starts from an empty board (skyline invariant) and equal
 // tiles are adjacent in its tile list.
+// Shared memory of one warp of the lane kernels: the tables of the problem state it is playing.
+template <int NB, int W, int EW>
+struct LaneTables {
+    static constexpr int WROWS = 32 * W + 1, HROWS = (1 << NB) + 1, NE = 32 * EW;
+    uint32_t wmask[WROWS * EW];
+    uint32_t hmask[HROWS * EW];
+    LaneEntry<W, EW> entries[NE];
+};
+
+// One work unit: chunks [chunk_begin, chunk_end) of child `entry` of problem `prob`.  The
+// problem's tables (shared memory) are refilled when `cached_key` (problem, depth) changes; the
+// child board is built once and every chunk writes its 8-byte record.
+// CG: the state may have been written by another warp of this launch (resident search).
+template <bool CG, int NB, int W, int EW>
+__device__ __forceinline__ void lanes_play_unit(const SearchParams& p, LaneTables<NB, W, EW>& tb,
+                                                const uint8_t* sel8, int prob, int entry,
+                                                int chunk_begin, int chunk_end, int& cached_key)
+{
+    constexpr int WROWS = LaneTables<NB, W, EW>::WROWS, HROWS = LaneTables<NB, W, EW>::HROWS,
+                  NE = LaneTables<NB, W, EW>::NE;
+    const int lane = lane_id();
+    const ProblemDesc d = p.desc[prob];
+    const int4 lfb = ld_state<CG>(p.lfb + prob);      // (hmin, col, run, live entries) of the parent
+    const int depth = ld_state<CG>(p.depth + prob);
+    const int key = prob | (depth << 24);
+
+    if (key != cached_key) {                          // tables of this problem's current state
+        __syncwarp();
+        const uint32_t* gw = p.wmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
+        const uint32_t* gh = p.hmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
+        for (int i = lane; i < WROWS * EW; i += 32) {
+            const int x = i / EW, q = i % EW;
+            tb.wmask[i] = (x <= d.cols) ? ld_state<CG>(gw + x * LANES_MASK_WORDS + q) : 0u;
+        }
+        // row inv of the shared table = entries with h <= rows - hmin, hmin = 2^NB - 1 - inv
+        for (int i = lane; i < HROWS * EW; i += 32) {
+            const int y = i / EW - ((1 << NB) - 1 - d.rows), q = i % EW;
+            tb.hmask[i] = (y >= 0 && y <= d.rows) ? ld_state<CG>(gh + y * LANES_MASK_WORDS + q) : 0u;
+        }
+        const uint4* gg = reinterpret_cast<const uint4*>(p.pairs) + (size_t)prob * p.es;
+        const uint4* gt = p.tile + (size_t)prob * p.es;
+        for (int i = lane; i < NE; i += 32) {
+            const bool in = i < d.n_entries;
+            const uint4 pr = in ? ld_state<CG>(gg + i) : make_uint4(0u, 0u, 0u, 0u);
+            const uint32_t pair[4] = {pr.x, pr.y, pr.z, pr.w};
+            tb.entries[i].set(in ? ld_state<CG>(gt + i) : make_uint4(0u, 0u, 0u, 0u), pair);
+        }
+        __syncwarp();
+        cached_key = key;
+    }
+
+    // the child: parent + entry placed at the parent's first free cell, pair removed
+    LaneBoard<NB, W, EW> s;
+    const uint32_t* gp = p.planes + (size_t)prob * LANES_PLANE_STRIDE;
+#pragma unroll
+    for (int b = 0; b < NB; ++b)
+#pragma unroll
+        for (int q = 0; q < W; ++q) s.pl[b][q] = ld_state<CG>(gp + b * 4 + q);
+#pragma unroll
+    for (int q = 0; q < EW; ++q) s.alive[q] = word_range(0, lfb.w, q);
+    const uint4 et = ld_state<CG>(p.tile + (size_t)prob * p.es + entry);
+    uint32_t foot[W];
+#pragma unroll
+    for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)et.y, q);
+    lanes_place(s, foot, lfb.x, lfb.x + (int)et.x);
+#pragma unroll
+    for (int q = 0; q < EW; ++q) s.alive[q] &= ~tb.entries[entry].pair(q);
+    const int n_alive = lfb.w - 2;
+    const uint32_t tag = ((uint32_t)depth << 16) | (uint32_t)entry;
+
+    for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
+        const int first = chunk * CHUNK;
+        const int count = min(CHUNK, p.n_local - first);
+        int my_solved;
+        const int my_steps = lanes_rollout<NB, W, EW>(
+            s, d.rows, n_alive, tb.wmask, tb.hmask, tb.entries, sel8, p.seed, d.stream, tag,
+            (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
+
+        const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved != 0);
+        const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
+        const int mx = __reduce_max_sync(FULLMASK, my_steps);
+        const int sum = __reduce_add_sync(FULLMASK, my_steps);
+        const int pre = __reduce_add_sync(FULLMASK, (lane <= first_lane) ? my_steps : 0);
+        if (lane == 0) {
+            ChunkRec r;
+            r.max_steps = (uint8_t)mx;
+            r.solved_lane = (uint8_t)first_lane;
+            r.sum_steps = (uint16_t)sum;
+            r.prefix_steps = (uint16_t)pre;
+            r.n_sims = (uint16_t)count;
+            p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
+        }
+    }
+}
+
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
 fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
 {
-    constexpr int WROWS = 32 * W + 1, HROWS = (1 << NB) + 1, NE = 32 * EW;
-    __shared__ uint32_t s_wmask[4][WROWS * EW];
-    __shared__ uint32_t s_hmask[4][HROWS * EW];
-    __shared__ LaneEntry<W, EW> s_entries[4][NE];
+    __shared__ LaneTables<NB, W, EW> s_tb[4];
     __shared__ uint8_t s_sel8[256 * 8];
     fill_select_table(s_sel8);
     __syncthreads();
@@ -190,7 +363,7 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     const int groups_per_child = (p.n_chunks + group - 1) / group;
     const unsigned long long n_units = (unsigned long long)n_children * groups_per_child;
     unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
-    int cached_prob = -1;
+    int cached_key = -1;
     for (;;) {
         unsigned long long unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
@@ -200,79 +373,8 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
         const int chunk_begin = (int)(unit % groups_per_child) * group;
         const int chunk_end = min(chunk_begin + group, p.n_chunks);
         const uint32_t packed = p.child_list[cls_list_offset + child];
-        const int prob = (int)(packed & 0xFFFFFFu);
-        const int entry = (int)(packed >> 24);
-        const ProblemDesc d = p.desc[prob];
-        const int4 lfb = p.lfb[prob];                 // (hmin, col, run, live entries) of the parent
-
-        if (prob != cached_prob) {                    // tables of this problem's current state
-            __syncwarp();
-            const uint32_t* gw = p.wmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
-            const uint32_t* gh = p.hmask + (size_t)prob * LANES_TABLE_ROWS * LANES_MASK_WORDS;
-            for (int i = lane; i < WROWS * EW; i += 32) {
-                const int x = i / EW, q = i % EW;
-                s_wmask[warp][i] = (x <= d.cols) ? gw[x * LANES_MASK_WORDS + q] : 0u;
-            }
-            // row inv of the shared table = entries with h <= rows - hmin, hmin = 2^NB - 1 - inv
-            for (int i = lane; i < HROWS * EW; i += 32) {
-                const int y = i / EW - ((1 << NB) - 1 - d.rows), q = i % EW;
-                s_hmask[warp][i] = (y >= 0 && y <= d.rows) ? gh[y * LANES_MASK_WORDS + q] : 0u;
-            }
-            const uint4* gg = reinterpret_cast<const uint4*>(p.pairs) + (size_t)prob * p.es;
-            const uint4* gt = p.tile + (size_t)prob * p.es;
-            for (int i = lane; i < NE; i += 32) {
-                const bool in = i < d.n_entries;
-                const uint4 pr = in ? gg[i] : make_uint4(0u, 0u, 0u, 0u);
-                const uint32_t pair[4] = {pr.x, pr.y, pr.z, pr.w};
-                s_entries[warp][i].set(in ? gt[i] : make_uint4(0u, 0u, 0u, 0u), pair);
-            }
-            __syncwarp();
-            cached_prob = prob;
-        }
-
-        // the child: parent + entry placed at the parent's first free cell, pair removed
-        LaneBoard<NB, W, EW> s;
-        const uint32_t* gp = p.planes + (size_t)prob * LANES_PLANE_STRIDE;
-#pragma unroll
-        for (int b = 0; b < NB; ++b)
-#pragma unroll
-            for (int q = 0; q < W; ++q) s.pl[b][q] = gp[b * 4 + q];
-#pragma unroll
-        for (int q = 0; q < EW; ++q) s.alive[q] = word_range(0, lfb.w, q);
-        const uint4 et = p.tile[(size_t)prob * p.es + entry];
-        uint32_t foot[W];
-#pragma unroll
-        for (int q = 0; q < W; ++q) foot[q] = word_range(lfb.y, lfb.y + (int)et.y, q);
-        lanes_place(s, foot, lfb.x, lfb.x + (int)et.x);
-#pragma unroll
-        for (int q = 0; q < EW; ++q) s.alive[q] &= ~s_entries[warp][entry].pair(q);
-        const int n_alive = lfb.w - 2;
-        const uint32_t tag = ((uint32_t)p.depth[prob] << 16) | (uint32_t)entry;
-
-        for (int chunk = chunk_begin; chunk < chunk_end; ++chunk) {
-            const int first = chunk * CHUNK;
-            const int count = min(CHUNK, p.n_local - first);
-            int my_solved;
-            const int my_steps = lanes_rollout<NB, W, EW>(
-                s, d.rows, n_alive, s_wmask[warp], s_hmask[warp], s_entries[warp], s_sel8,
-                p.seed, d.stream, tag,
-                (uint32_t)(p.sim_begin + first + lane), lane < count ? 1 : 0, my_solved);
-
-            const uint32_t solved_mask = __ballot_sync(FULLMASK, my_solved != 0);
-            const int first_lane = solved_mask ? (__ffs(solved_mask) - 1) : 0xFF;
-            const int mx = __reduce_max_sync(FULLMASK, my_steps);
-            const int sum = __reduce_add_sync(FULLMASK, my_steps);
-            const int pre = __reduce_add_sync(FULLMASK, (lane <= first_lane) ? my_steps : 0);
-            if (lane == 0) {
-                ChunkRec r;
-                r.max_steps = (uint8_t)mx;
-                r.solved_lane = (uint8_t)first_lane;
-                r.sum_steps = (uint16_t)sum;
-                r.prefix_steps = (uint16_t)pre;
-                r.n_sims = (uint16_t)count;
-                p.rec[((size_t)prob * p.es + entry) * p.n_chunks + chunk] = r;
-            }
-        }
+        lanes_play_unit<false>(p, s_tb[warp], s_sel8, (int)(packed & 0xFFFFFFu), (int)(packed >> 24),
+                               chunk_begin, chunk_end, cached_key);
     }
 }
 
@@ -384,6 +486,7 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
 
 // --------------------------------------------------------- per-child statistics
 // this rank's statistics of child `entry` of problem `prob`, from its chunk records
+template <bool CG>
 __device__ __forceinline__ ChildStats stats_from_records(const SearchParams& p, int prob, int entry)
 {
     const ChunkRec* rec = p.rec + ((size_t)prob * p.es + entry) * p.n_chunks;
@@ -394,7 +497,9 @@ __device__ __forceinline__ ChildStats stats_from_records(const SearchParams& p, 
     st.prefix_steps = 0;
 #pragma unroll 8
     for (int ch = 0; ch < p.n_chunks; ++ch) {          // independent 8-byte loads, 8 in flight
-        const ChunkRec r = rec[ch];
+        const uint2 raw = ld_state<CG>(reinterpret_cast<const uint2*>(rec + ch));
+        ChunkRec r;
+        memcpy(&r, &raw, sizeof(r));
         st.max_steps = max(st.max_steps, (int)r.max_steps);
         st.sum_steps += r.sum_steps;
         if (st.first_solved == NONE_U32) {
@@ -446,15 +551,12 @@ fs_reduce_kernel(SearchParams p, const int* __restrict__ cls_problems, int n_cls
     for (int j = 0; j < EJ; ++j) {
         if ((legal[j] >> lane) & 1u) {
             const int e = lane + 32 * j;
-            p.stats[(size_t)prob * p.es + e] = stats_from_records(p, prob, e);
+            p.stats[(size_t)prob * p.es + e] = stats_from_records<false>(p, prob, e);
         }
     }
 }
 
-// ------------------------------------------------------------------ advance kernel
-// One warp per problem.  FIRST: set up depth 0.  Otherwise: score the children of the
-// current depth (lane = child), stop at the first child with a solved rollout, else commit
-// the first maximum; then expand the new state (LFB, legal entries, child list).
+// compacted live tile list (order kept) through a shared-memory buffer of the warp
 template <int RHO, int W, int EJ>
 __device__ __forceinline__ void compact_entries_adv(WarpState<RHO, W, EJ>& s, uint16_t* buf)
 {
@@ -476,17 +578,75 @@ __device__ __forceinline__ void compact_entries_adv(WarpState<RHO, W, EJ>& s, ui
     __syncwarp();
 }
 
-template <int RHO, int W, int EJ, bool FIRST>
-__global__ void __launch_bounds__(ADV_WARPS * 32)
-fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
-                  const int* __restrict__ cls_problems, int n_cls_problems, int next_slot,
-                  const ChildStats* __restrict__ gathered)
+// ---- resident search: publish the units of a problem's new depth ------------------------
+// Called by a whole warp after the problem's state, legal mask and lane tables are written.
+// `ebuf` (shared, >= 32 * EJ entries) receives the legal entries in table order.
+template <int EJ>
+__device__ __forceinline__ void publish_units(const SearchParams& p, UnitQueue* q, UnitSlot* slots,
+                                              int prob, const uint32_t (&legal)[EJ], int k,
+                                              uint16_t* ebuf, unsigned n_warps)
 {
-    __shared__ uint16_t cbuf[ADV_WARPS][32 * EJ];
-    const int warp = threadIdx.x >> 5;
-    const int idx = blockIdx.x * ADV_WARPS + warp;
-    if (idx >= n_cls_problems) return;
-    const int prob = cls_problems[idx];
+    const int lane = lane_id();
+    const uint32_t lt = (1u << lane) - 1u;
+    __syncwarp();
+    int base = 0;
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) {
+        if ((legal[j] >> lane) & 1u) ebuf[base + __popc(legal[j] & lt)] = (uint16_t)(lane + 32 * j);
+        base += __popc(legal[j]);
+    }
+    __syncwarp();
+    // Unit size: whole children while the problems in flight offer >= 2 units per resident warp,
+    // single chunks when few problems are left (their critical path is what remains).
+    // (read by one lane: the count changes under our feet and every lane must agree on the split)
+    const int in_flight = max(__shfl_sync(FULLMASK, ld_volatile(&q->in_flight), 0), 1);
+    const long long want = (long long)in_flight * k * p.n_chunks / (2ll * n_warps);
+    const int group_min = (p.n_chunks + MAX_UNITS_PER_CHILD - 1) / MAX_UNITS_PER_CHILD;
+    int group = (int)min((long long)p.n_chunks, max((long long)group_min, want));
+    if (p.res_flags & 1) group = group_min;
+    const int gpc = (p.n_chunks + group - 1) / group;
+    group = (p.n_chunks + gpc - 1) / gpc;                      // equal units
+    const int n_units = k * gpc;
+    unsigned long long t0 = 0;
+    if (lane == 0) {
+        st_volatile(p.pending + prob, n_units);
+        t0 = atomicAdd(&q->tail, (unsigned long long)n_units);
+        const int est = ld_volatile(&q->est_units);
+        st_volatile(&q->est_units, est == 0 ? n_units : (est * 7 + n_units + 7) / 8);   // racy by design
+    }
+    t0 = __shfl_sync(FULLMASK, t0, 0);
+    const unsigned mask = q->cap_mask;
+    for (int i = lane; i < n_units; i += 32) {
+        const int ci = i / gpc, g = i - ci * gpc;
+        UnitSlot* sl = slots + ((t0 + i) & mask);
+        st_volatile(&sl->child, (uint32_t)prob | ((uint32_t)ebuf[ci] << 24));
+        st_volatile(&sl->chunk_begin, (uint32_t)(g * group));
+        st_volatile(&sl->chunk_count, (uint32_t)min(group, p.n_chunks - g * group));
+    }
+    // state, tables, pending and payloads before any seq: every lane fences its own writes,
+    // the warp barrier orders them before the seq stores of all lanes
+    __threadfence();
+    __syncwarp();
+    for (int i = lane; i < n_units; i += 32)
+        st_volatile(&slots[(t0 + i) & mask].seq, (uint32_t)(t0 + i + 1));
+    __syncwarp();
+}
+
+// ------------------------------------------------------------------ advance
+// One warp, one problem.  FIRST: set up depth 0.  Otherwise: score the children of the
+// current depth (lane = child), stop at the first child with a solved rollout, else commit
+// the first maximum; then expand the new state (LFB, legal entries, lane tables) and hand the
+// children of the next depth to the rollout kernels: appended to the class's child list
+// (one launch per depth) or, RESIDENT, published as units on the queue.
+// Returns the problem's status.
+template <int RHO, int W, int EJ, bool FIRST, bool RESIDENT>
+__device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, int cls,
+                                               int cls_list_offset, int next_slot,
+                                               const ChildStats* __restrict__ gathered,
+                                               uint16_t* cbuf, UnitQueue* q, UnitSlot* slots,
+                                               unsigned n_warps)
+{
+    constexpr bool CG = RESIDENT;
     const int lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     const ProblemDesc d = p.desc[prob];
@@ -494,19 +654,19 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
     WarpState<RHO, W, EJ> s;
     int n_alive;
     if (FIRST) {
-        load_board(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
-        load_entries(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
-        compact_entries_adv(s, cbuf[warp]);
+        load_board_t<CG>(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
+        load_entries_t<CG>(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
+        compact_entries_adv(s, cbuf);
         n_alive = count_alive(s);
     } else {
-        if (p.status[prob] != ST_ACTIVE) return;
-        const int depth = p.depth[prob];
-        const int4 lfb = p.lfb[prob];
+        if (ld_state<CG>(p.status + prob) != ST_ACTIVE) return ST_DEAD;
+        const int depth = ld_state<CG>(p.depth + prob);
+        const int4 lfb = ld_state<CG>(p.lfb + prob);
         n_alive = lfb.w;
-        const uint4 lg = p.legal[prob];
+        const uint4 lg = ld_state<CG>(p.legal + prob);
         const uint32_t legal[4] = {lg.x, lg.y, lg.z, lg.w};
-        load_board(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
-        load_entries(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
+        load_board_t<CG>(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
+        load_entries_t<CG>(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
 
         // ---- per-child statistics, lane = child ---------------------------------
         ChildStats st[EJ];
@@ -520,7 +680,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
             st[j].sum_steps = 0; st[j].prefix_steps = 0;
             if (is_child)
                 st[j] = gathered ? stats_from_gathered(p, gathered, prob, e)
-                                 : stats_from_records(p, prob, e);
+                                 : stats_from_records<CG>(p, prob, e);
             solved_m[j] = __ballot_sync(FULLMASK, is_child && st[j].first_solved != NONE_U32);
             if (first_child < 0 && solved_m[j]) first_child = 32 * j + __ffs(solved_m[j]) - 1;
         }
@@ -559,11 +719,11 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
         roll = warp_sum_ll(roll);
         plc = warp_sum_ll(plc);
         plc_exec = warp_sum_ll(plc_exec);
-        if (lane == 0) {
-            p.placements_executed[prob] += (unsigned long long)plc_exec;
-            p.rollouts[prob] += (unsigned long long)roll;
-            p.rollout_placements[prob] += (unsigned long long)plc;
-            p.n_tiles_placed[prob] += (unsigned long long)plc;
+        if (lane == 0) {        // only this problem's advancing warp touches these; L2 atomics
+            atomicAdd(p.placements_executed + prob, (unsigned long long)plc_exec);
+            atomicAdd(p.rollouts + prob, (unsigned long long)roll);
+            atomicAdd(p.rollout_placements + prob, (unsigned long long)plc);
+            atomicAdd(p.n_tiles_placed + prob, (unsigned long long)plc);
         }
 
         const int take = first_child >= 0 ? first_child : best_entry;
@@ -571,8 +731,8 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
 #pragma unroll
         for (int j = 1; j < EJ; ++j) mine = ((take >> 5) == j) ? s.ent[j] : mine;
         const uint32_t v = __shfl_sync(FULLMASK, mine, take & 31);
-        const uint16_t prev = p.prev_tile[prob];
-        int n_order = p.n_order[prob];
+        const uint16_t prev = ld_state<CG>(p.prev_tile + prob);
+        int n_order = ld_state<CG>(p.n_order + prob);
         uint8_t* order = p.order + (size_t)prob * (p.es / 2 + 2) * 2;
 
         place(s, lfb.x, lfb.y, (int)(v & 0xFFu), (int)(v >> 8));
@@ -582,7 +742,8 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
             // ---- solved inside a rollout (MCTS.py:77-93) -------------------------
             if (lane == 0) {
                 // entries after the solving child were never attempted (:58-60)
-                p.n_tiles_placed[prob] -= (unsigned long long)(n_alive - first_child - 1);
+                atomicAdd(p.n_tiles_placed + prob,
+                          0ull - (unsigned long long)(n_alive - first_child - 1));
                 if (prev) { order[2 * n_order] = prev & 0xFF; order[2 * n_order + 1] = prev >> 8; n_order++; }
                 order[2 * n_order] = v & 0xFF; order[2 * n_order + 1] = v >> 8; n_order++;
             }
@@ -602,11 +763,11 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
                 p.n_order[prob] = n_order + steps;
                 p.status[prob] = solved ? ST_SOLVED : ST_DEAD;   // solved is always true here
             }
-            return;
+            return solved ? ST_SOLVED : ST_DEAD;
         }
 
         // ---- commit the best child (MCTS.py:105-119) -----------------------------
-        compact_entries_adv(s, cbuf[warp]);
+        compact_entries_adv(s, cbuf);
         n_alive -= 2;
         if (lane == 0) {
             if (prev) { order[2 * n_order] = prev & 0xFF; order[2 * n_order + 1] = prev >> 8; n_order++; }
@@ -641,22 +802,219 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
                               EJ > 2 ? legal[EJ > 2 ? 2 : 0] : 0u, EJ > 3 ? legal[EJ > 3 ? 3 : 0] : 0u);
         p.legal[prob] = lg;
         if (status != ST_SOLVED && n_alive > 0 && r >= 0)
-            p.n_tiles_placed[prob] += (unsigned long long)n_alive;   // one attempt per entry (:60)
+            atomicAdd(p.n_tiles_placed + prob, (unsigned long long)n_alive);   // one attempt per entry (:60)
         if (k > 0) {
-            base = atomicAdd(&p.child_count[next_slot * FS_CLASSES + cls], (unsigned)k);
-            p.rollouts_executed[prob] += (unsigned long long)k * p.n_local;
+            if (!RESIDENT) base = atomicAdd(&p.child_count[next_slot * FS_CLASSES + cls], (unsigned)k);
+            atomicAdd(p.rollouts_executed + prob, (unsigned long long)k * p.n_local);
         }
     }
     if (k > 0) {
-        base = __shfl_sync(FULLMASK, base, 0);
+        if (!RESIDENT) {
+            base = __shfl_sync(FULLMASK, base, 0);
 #pragma unroll
-        for (int j = 0; j < EJ; ++j) {
-            if ((legal[j] >> lane) & 1u)
-                p.child_list[cls_list_offset + base + __popc(legal[j] & lt)] =
-                    (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
-            base += __popc(legal[j]);
+            for (int j = 0; j < EJ; ++j) {
+                if ((legal[j] >> lane) & 1u)
+                    p.child_list[cls_list_offset + base + __popc(legal[j] & lt)] =
+                        (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
+                base += __popc(legal[j]);
+            }
         }
         if (p.use_lanes) write_lane_tables(p, prob, d, s, n_alive);
+        if (RESIDENT) publish_units<EJ>(p, q, slots, prob, legal, k, cbuf, n_warps);
+    }
+    return status;
+}
+
+template <int RHO, int W, int EJ, bool FIRST>
+__global__ void __launch_bounds__(ADV_WARPS * 32)
+fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
+                  const int* __restrict__ cls_problems, int n_cls_problems, int next_slot,
+                  const ChildStats* __restrict__ gathered)
+{
+    __shared__ uint16_t cbuf[ADV_WARPS][32 * EJ];
+    const int warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * ADV_WARPS + warp;
+    if (idx >= n_cls_problems) return;
+    advance_problem<RHO, W, EJ, FIRST, false>(p, cls_problems[idx], cls, cls_list_offset, next_slot,
+                                              gathered, cbuf[warp], nullptr, nullptr, 0u);
+}
+
+// Out of line on purpose: the resident kernel is compiled under the register cap of its rollout
+// loop (resident_blocks), and the advance -- which runs once per problem and depth -- keeps its
+// own, larger working set (spilling if it must) without costing the loop a register.
+template <int RHO, int W, int EJ>
+__device__ __noinline__ int advance_resident(const SearchParams& p, int prob, uint16_t* cbuf,
+                                             UnitQueue* q, UnitSlot* slots, unsigned n_warps)
+{
+    return advance_problem<RHO, W, EJ, false, true>(p, prob, 0, 0, 0, nullptr, cbuf, q, slots, n_warps);
+}
+
+// resident blocks per SM = what the rollout loop alone (fs_rollout_lanes_kernel) reaches
+constexpr int resident_blocks(int nb, int w, int ew)
+{
+    const int wi = w == 1 ? 0 : (w == 2 ? 1 : 2), ei = ew == 4 ? 1 : 0;
+    constexpr int tab[4][3][2] = {{{9, 8}, {8, 7}, {5, 5}},
+                                  {{9, 8}, {7, 7}, {5, 4}},
+                                  {{9, 7}, {7, 6}, {4, 4}},
+                                  {{9, 6}, {7, 5}, {4, 4}}};
+    return tab[nb - 5][wi][ei];
+}
+
+// ------------------------------------------------------- resident search kernel
+// The whole flat search of one search class in ONE launch.  Persistent warps take units from
+// the class queue and play them (lanes_play_unit); the warp that completes the last unit of a
+// problem's depth advances that problem itself (advance_problem) and publishes the units of
+// its next depth.  Problems therefore move through their depths independently: no per-depth
+// launches, no barrier between depths, no tail per depth.
+//   * visibility: records / state / tables written by one warp are read by another inside
+//     the same launch, so those reads go through L2 (ld.global.cg) and every hand-over is
+//     fence -> atomic / volatile flag -> fence.
+//   * leaving: a warp that is about to wait while more warps are already waiting than the
+//     problems in flight can feed leaves the kernel, so the SM slots go to the next class's
+//     kernel queued on another stream; everyone leaves when no problem is in flight.
+//   * watchdog: a warp that waits ~seconds for its slot raises `abort`; the host reports it.
+template <int NB, int RHO, int W, int EJ>
+__global__ void __launch_bounds__(128, resident_blocks(NB, W, EJ))
+fs_search_resident_kernel(SearchParams p, UnitQueue* q, UnitSlot* slots,
+                          const int* __restrict__ cls_problems, int n_cls_problems)
+{
+    constexpr int EW = EJ;
+    static_assert(EJ == 2 || EJ == 4, "entry words of the lane kernel");
+    __shared__ LaneTables<NB, W, EW> s_tb[4];
+    __shared__ uint8_t s_sel8[256 * 8];
+    __shared__ uint16_t s_cbuf[4][32 * EJ];
+    fill_select_table(s_sel8);
+    __syncthreads();
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const unsigned n_warps = gridDim.x * 4u;
+
+    // ---- prologue: publish depth 0 (state and tables were written by bp_search_reset) -----
+    for (;;) {
+        unsigned idx = 0;
+        if (lane == 0) idx = atomicAdd(&q->init_next, 1u);
+        idx = __shfl_sync(FULLMASK, idx, 0);
+        if (idx >= (unsigned)n_cls_problems) break;
+        const int prob = cls_problems[idx];
+        const uint4 lg = p.legal[prob];
+        const uint32_t lgw[4] = {lg.x, lg.y, lg.z, lg.w};
+        uint32_t legal[EJ];
+        int k = 0;
+#pragma unroll
+        for (int j = 0; j < EJ; ++j) { legal[j] = lgw[j]; k += __popc(legal[j]); }
+        if (p.status[prob] == ST_ACTIVE && k > 0)
+            publish_units<EJ>(p, q, slots, prob, legal, k, s_cbuf[warp], n_warps);
+        else if (lane == 0)
+            atomicSub(&q->in_flight, 1);
+        if (lane == 0) { __threadfence(); atomicAdd(&q->init_done, 1u); }
+    }
+    if (lane == 0) {
+        unsigned spins = 0;
+        while (ld_volatile(&q->init_done) < (unsigned)n_cls_problems && !ld_volatile(&q->abort)) {
+            __nanosleep(1000);
+            if (++spins > (1u << 22)) st_volatile(&q->abort, 1);
+        }
+    }
+    __syncwarp();
+
+    int cached_key = -1;
+    bool waited = true;          // lane 0: the previous ticket was not ready when taken
+    const long long c_begin = clock64();
+    long long c_wait = 0, c_play = 0, c_adv = 0;
+    unsigned n_played = 0, n_adv = 0;
+    for (;;) {
+        // ---- take a ticket, or leave ----------------------------------------------------
+        // (the leave rule reads the queue's hot lines, so only a warp that just had to wait
+        // for work evaluates it)
+        unsigned long long ticket = 0;
+        int leave = 0;
+        if (lane == 0) {
+            if (waited) {
+                const int in_flight = ld_volatile(&q->in_flight);
+                if (in_flight <= 0 || ld_volatile(&q->abort)) {
+                    leave = 1;
+                } else {
+                    const long long waiters =
+                        (long long)(ld_volatile(&q->head) - ld_volatile(&q->tail));
+                    const long long feed = 2ll * in_flight * max(ld_volatile(&q->est_units), 1) + 4;
+                    if (waiters >= feed && !(p.res_flags & 2)) leave = 1;
+                }
+            }
+            if (!leave) ticket = atomicAdd(&q->head, 1ull);
+        }
+        leave = __shfl_sync(FULLMASK, leave, 0);
+        if (leave) break;
+        ticket = __shfl_sync(FULLMASK, ticket, 0);
+
+        // ---- wait for the slot ------------------------------------------------------------
+        const long long c0 = clock64();
+        UnitSlot* sl = slots + (ticket & q->cap_mask);
+        const uint32_t want = (uint32_t)(ticket + 1);
+        uint4 unit = make_uint4(0u, 0u, 0u, 0u);
+        if (lane == 0) {
+            // poll this ticket's own slot; the shared flags only every 16th time (thousands of
+            // idle warps hammering one line would starve the atomics of the working ones)
+            unsigned spins = 0, ns = 64;
+            waited = false;
+            for (;;) {
+                if (ld_volatile(&sl->seq) == want) {
+                    __threadfence();
+                    unit.y = ld_volatile(&sl->child);
+                    unit.z = ld_volatile(&sl->chunk_begin);
+                    unit.w = ld_volatile(&sl->chunk_count);
+                    __threadfence();
+                    if (ld_volatile(&sl->seq) != want) st_volatile(&q->abort, 2);   // ring overrun
+                    unit.x = 1u;
+                    break;
+                }
+                if ((spins & 15u) == 15u &&
+                    (ld_volatile(&q->in_flight) <= 0 || ld_volatile(&q->abort))) break;
+                waited = true;
+                __nanosleep(ns);
+                if (ns < 4096) ns *= 2;
+                if (++spins > (1u << 21)) { st_volatile(&q->abort, 1); break; }
+            }
+        }
+        unit.x = __shfl_sync(FULLMASK, unit.x, 0);
+        if (!unit.x) break;
+        unit.y = __shfl_sync(FULLMASK, unit.y, 0);
+        unit.z = __shfl_sync(FULLMASK, unit.z, 0);
+        unit.w = __shfl_sync(FULLMASK, unit.w, 0);
+        const int prob = (int)(unit.y & 0xFFFFFFu), entry = (int)(unit.y >> 24);
+        const long long c1 = clock64();
+        c_wait += c1 - c0;
+
+        lanes_play_unit<true>(p, s_tb[warp], s_sel8, prob, entry, (int)unit.z, (int)(unit.z + unit.w),
+                              cached_key);
+
+        // ---- the last unit of this problem's depth advances it ----------------------------
+        int last = 0;
+        if (lane == 0) {
+            __threadfence();                                   // records before the count
+            last = atomicSub(p.pending + prob, 1) == 1;
+        }
+        last = __shfl_sync(FULLMASK, last, 0);
+        const long long c2 = clock64();
+        c_play += c2 - c1;
+        n_played++;
+        if (last) {
+            __threadfence();
+            const int status = advance_resident<RHO, W, EJ>(p, prob, s_cbuf[warp], q, slots, n_warps);
+            if (status != ST_ACTIVE && lane == 0) {
+                __threadfence();
+                atomicSub(&q->in_flight, 1);
+            }
+            c_adv += clock64() - c2;
+            n_adv++;
+        }
+    }
+    if (lane == 0) {
+        atomicAdd(&q->cyc_total, (unsigned long long)(clock64() - c_begin));
+        atomicAdd(&q->cyc_wait, (unsigned long long)c_wait);
+        atomicAdd(&q->cyc_play, (unsigned long long)c_play);
+        atomicAdd(&q->cyc_advance, (unsigned long long)c_adv);
+        atomicAdd(&q->n_units_played, (unsigned long long)n_played);
+        atomicAdd(&q->n_advances, (unsigned long long)n_adv);
     }
 }
 
@@ -687,6 +1045,37 @@ static void dispatch_lanes(int scls, F&& f)
         case 6: with_w(IC<6>{}); break;
         case 7: with_w(IC<7>{}); break;
         default: with_w(IC<8>{}); break;
+    }
+}
+
+// resident-kernel instantiation of a resident class index: ((nb - 5) * 3 + w index) * 2 + (EW == 4)
+constexpr int RS_CLASSES = 24;
+static int resident_class_of(int scls)
+{
+    const int cls = scls % N_CLASSES, nb = 5 + scls / N_CLASSES;
+    const int ej = cls % 3, w = (cls / 3) % 3;
+    return ((nb - 5) * 3 + w) * 2 + (ej == 2 ? 1 : 0);
+}
+// f(IC<NB>, IC<RHO>, IC<W>, IC<EJ>)
+template <typename F>
+static void dispatch_resident(int rcls, F&& f)
+{
+    const int ew = rcls % 2, w = (rcls / 2) % 3, nb = 5 + rcls / 6;
+    auto with_ew = [&](auto NBc, auto R, auto Wc) {
+        if (ew == 0) f(NBc, R, Wc, IC<2>{}); else f(NBc, R, Wc, IC<4>{});
+    };
+    auto with_w = [&](auto NBc, auto R) {
+        switch (w) {
+            case 0: with_ew(NBc, R, IC<1>{}); break;
+            case 1: with_ew(NBc, R, IC<2>{}); break;
+            default: with_ew(NBc, R, IC<4>{}); break;
+        }
+    };
+    switch (nb) {
+        case 5: with_w(IC<5>{}, IC<1>{}); break;
+        case 6: with_w(IC<6>{}, IC<2>{}); break;
+        case 7: with_w(IC<7>{}, IC<4>{}); break;
+        default: with_w(IC<8>{}, IC<4>{}); break;
     }
 }
 
@@ -725,11 +1114,29 @@ struct bp_search {
     std::vector<cudaEvent_t> cls_done;
     std::vector<int> cls_depth;
     cudaEvent_t fork_ev = nullptr;
+    // resident search (one launch per resident class): queues, rings, problem lists
+    int mode = BP_SEARCH_AUTO;
+    bool ran_resident = false;
+    std::vector<int> rclasses;                  // resident classes present
+    int rcls_count[RS_CLASSES] = {0};
+    int rcls_prob_off[RS_CLASSES] = {0};
+    size_t rcls_slot_off[RS_CLASSES] = {0};
+    int grid_resident[RS_CLASSES] = {0};
+    std::vector<UnitQueue> h_queues;            // initial queue headers
+    int* d_rcls_problems = nullptr;
+    UnitQueue* d_queues = nullptr;              // [RS_CLASSES]
+    UnitQueue* d_queues_init = nullptr;
+    UnitSlot* d_slots = nullptr;
+    size_t n_slots = 0;
+    std::vector<cudaStream_t> rcls_stream;
+    std::vector<cudaEvent_t> rcls_done;
     ~bp_search()
     {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
         for (cudaStream_t st : cls_stream) cudaStreamDestroy(st);
         for (cudaEvent_t e : cls_done) cudaEventDestroy(e);
+        for (cudaStream_t st : rcls_stream) cudaStreamDestroy(st);
+        for (cudaEvent_t e : rcls_done) cudaEventDestroy(e);
         if (fork_ev) cudaEventDestroy(fork_ev);
     }
 };
@@ -845,6 +1252,32 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         }
     }
     p.use_lanes = lanes_ok ? 1 : 0;
+    if (const char* env = getenv("BP_RESIDENT_FLAGS")) p.res_flags = atoi(env);
+
+    // resident classes: problem lists, ring capacities (every unit that can be outstanding)
+    std::vector<int> rcls_problems;
+    s->h_queues.assign(RS_CLASSES, UnitQueue{});
+    if (p.use_lanes) {
+        std::vector<std::vector<int>> by_rcls(RS_CLASSES);
+        for (int i = 0; i < n_problems; ++i) by_rcls[resident_class_of(s->h_desc[i].cls)].push_back(i);
+        const size_t upc = (size_t)std::min(p.n_chunks, MAX_UNITS_PER_CHILD);
+        for (int c = 0; c < RS_CLASSES; ++c) {
+            s->rcls_count[c] = (int)by_rcls[c].size();
+            s->rcls_prob_off[c] = (int)rcls_problems.size();
+            s->rcls_slot_off[c] = s->n_slots;
+            if (!s->rcls_count[c]) continue;
+            s->rclasses.push_back(c);
+            rcls_problems.insert(rcls_problems.end(), by_rcls[c].begin(), by_rcls[c].end());
+            size_t need = 0;
+            for (int i : by_rcls[c]) need += (size_t)s->h_desc[i].n_entries * upc;
+            size_t cap = 1024;
+            while (cap < need) cap <<= 1;
+            s->n_slots += cap;
+            UnitQueue& q = s->h_queues[c];
+            q.in_flight = s->rcls_count[c];
+            q.cap_mask = (unsigned)(cap - 1);
+        }
+    }
 
     int rc = BP_OK;
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
@@ -883,6 +1316,13 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             TRY(dev_alloc(s, &p.tile, P * p.es));
             TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
             TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+        }
+        if (p.use_lanes) {
+            TRY(dev_alloc(s, &p.pending, P));
+            TRY(dev_alloc(s, &s->d_rcls_problems, rcls_problems.size()));
+            TRY(dev_alloc(s, &s->d_queues, (size_t)RS_CLASSES));
+            TRY(dev_alloc(s, &s->d_queues_init, (size_t)RS_CLASSES));
+            TRY(dev_alloc(s, &s->d_slots, s->n_slots));
         }
         TRY(dev_alloc(s, &p.rec, P * p.es * (size_t)p.n_chunks));
         return BP_OK;
@@ -931,6 +1371,12 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     if (boards)
         BP_CUDA(cudaMemcpyAsync(s->d_init_occ, s->h_boards.data(), P * p.rs * p.ws * 4,
                                 cudaMemcpyHostToDevice, ctx->stream));
+    if (p.use_lanes) {
+        BP_CUDA(cudaMemcpyAsync(s->d_rcls_problems, rcls_problems.data(), rcls_problems.size() * sizeof(int),
+                                cudaMemcpyHostToDevice, ctx->stream));
+        BP_CUDA(cudaMemcpyAsync(s->d_queues_init, s->h_queues.data(), RS_CLASSES * sizeof(UnitQueue),
+                                cudaMemcpyHostToDevice, ctx->stream));
+    }
     BP_CUDA(cudaStreamSynchronize(ctx->stream));
 
     // persistent grid per class: every SM filled to the occupancy limit of that kernel
@@ -952,6 +1398,23 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             });
             s->grid_lanes[c] = ctx->sm_count * std::max(per_sm_l, 1);
         }
+    }
+    for (int c : s->rclasses) {
+        int per_sm = 1;
+        dispatch_resident(c, [&](auto NBc, auto R, auto Wc, auto E) {
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                &per_sm,
+                fs_search_resident_kernel<decltype(NBc)::value, decltype(R)::value, decltype(Wc)::value,
+                                          decltype(E)::value>,
+                128, 0);
+        });
+        s->grid_resident[c] = ctx->sm_count * std::max(per_sm, 1);
+        cudaStream_t st;
+        cudaEvent_t e;
+        BP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        BP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        s->rcls_stream.push_back(st);
+        s->rcls_done.push_back(e);
     }
     BP_CUDA(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
     for (int c : s->classes) {
@@ -1065,8 +1528,15 @@ int bp_search_reset(bp_search* s)
     BP_CUDA(cudaMemsetAsync(p.child_scores, 0xFF, P * (p.es / 2) * p.es * sizeof(int), st));
     BP_CUDA(cudaMemsetAsync(p.child_count, 0, s->counters_bytes, st));
     BP_CUDA(cudaMemsetAsync(p.task_counter, 0, s->counters_bytes, st));
+    if (p.use_lanes) {
+        BP_CUDA(cudaMemcpyAsync(s->d_queues, s->d_queues_init, RS_CLASSES * sizeof(UnitQueue),
+                                cudaMemcpyDeviceToDevice, st));
+        BP_CUDA(cudaMemsetAsync(s->d_slots, 0, s->n_slots * sizeof(UnitSlot), st));
+        BP_CUDA(cudaMemsetAsync(p.pending, 0, P * sizeof(int), st));
+    }
     launch_advance<true>(s, 0, nullptr);
     BP_CUDA(cudaGetLastError());
+    s->ran_resident = false;
     s->cur_depth = 0;
     s->ev_depths = 0;
     s->ready = true;
@@ -1079,9 +1549,17 @@ int bp_search_set_profiling(bp_search* s, int on)
     BP_CUDA(cudaSetDevice(s->ctx->device));
     s->profiling = on != 0;
     if (s->profiling && s->ev.empty()) {
-        s->ev.resize((size_t)3 * (s->max_depth + 1));
+        s->ev.resize((size_t)3 * std::max(s->max_depth + 1, RS_CLASSES));
         for (cudaEvent_t& e : s->ev) BP_CUDA(cudaEventCreate(&e));
     }
+    return BP_OK;
+}
+
+int bp_search_set_mode(bp_search* s, int mode)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    BP_REQUIRE(mode == BP_SEARCH_AUTO || mode == BP_SEARCH_STEPPED || mode == BP_SEARCH_RESIDENT, "mode");
+    s->mode = mode;
     return BP_OK;
 }
 
@@ -1099,7 +1577,7 @@ int bp_search_profile(bp_search* s, double* rollout_ms, double* advance_ms, int*
         a += ms;
     }
     *rollout_ms = r;
-    *advance_ms = a;
+    *advance_ms = s->ran_resident ? 0.0 : a;
     *n_depths = s->ev_depths;
     return BP_OK;
 }
@@ -1173,6 +1651,36 @@ int bp_search_info(bp_search* s, int* lane_kernel, int* n_classes)
     return BP_OK;
 }
 
+int bp_search_last_run(bp_search* s, int* resident)
+{
+    BP_REQUIRE(s && resident, "null argument");
+    *resident = s->ran_resident ? 1 : 0;
+    return BP_OK;
+}
+
+int bp_search_resident_stats(bp_search* s, double* out8)
+{
+    BP_REQUIRE(s && out8, "null argument");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    BP_CUDA(cudaStreamSynchronize(s->ctx->stream));
+    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    if (!s->ran_resident) return BP_OK;
+    std::vector<UnitQueue> queues(RS_CLASSES);
+    BP_CUDA(cudaMemcpy(queues.data(), s->d_queues, RS_CLASSES * sizeof(UnitQueue), cudaMemcpyDeviceToHost));
+    for (int c : s->rclasses) {
+        const UnitQueue& q = queues[c];
+        out8[0] += (double)q.cyc_total;
+        out8[1] += (double)q.cyc_wait;
+        out8[2] += (double)q.cyc_play;
+        out8[3] += (double)q.cyc_advance;
+        out8[4] += (double)q.n_units_played;
+        out8[5] += (double)q.n_advances;
+        out8[6] += (double)q.head;
+        out8[7] += (double)q.tail;
+    }
+    return BP_OK;
+}
+
 int bp_search_max_depth(bp_search* s, int* max_depth)
 {
     BP_REQUIRE(s && max_depth, "null argument");
@@ -1186,6 +1694,62 @@ int bp_search_run(bp_search* s)
     if (s->p.n_ranks != 1) {
         set_error("bp_search_run is single-rank; use the step API with a partition");
         return BP_ERR_STATE;
+    }
+    // AUTO = the faster form on this hardware, measured: launch-per-depth
+    int mode = s->mode;
+    if (const char* env = getenv("BP_SEARCH")) {
+        if (strcmp(env, "resident") == 0) mode = BP_SEARCH_RESIDENT;
+        else if (strcmp(env, "stepped") == 0) mode = BP_SEARCH_STEPPED;
+    }
+    if (mode == BP_SEARCH_RESIDENT && !s->p.use_lanes) {
+        set_error("the resident search kernel needs the lane kernel (empty initial boards, equal "
+                  "tiles adjacent in every list; BP_ROLLOUT != warp)");
+        return BP_ERR_STATE;
+    }
+    if (mode == BP_SEARCH_RESIDENT) {
+        // resident search: one launch per resident class, each on its own stream (the block
+        // scheduler hands the SM slots of warps that leave one class's kernel to the next);
+        // when profiling, serially on the caller's stream with an event pair around each
+        if (!s->ready || s->cur_depth != 0) {
+            set_error("bp_search_run: call bp_search_reset first");
+            return BP_ERR_STATE;
+        }
+        BP_CUDA(cudaSetDevice(s->ctx->device));
+        const bool fork = !s->profiling && s->rclasses.size() > 1;
+        if (fork) {
+            BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
+            for (size_t k = 0; k < s->rclasses.size(); ++k)
+                BP_CUDA(cudaStreamWaitEvent(s->rcls_stream[k], s->fork_ev, 0));
+        }
+        for (size_t k = 0; k < s->rclasses.size(); ++k) {
+            const int c = s->rclasses[k];
+            cudaStream_t st = fork ? s->rcls_stream[k] : s->ctx->stream;
+            if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * k], st));
+            dispatch_resident(c, [&](auto NBc, auto R, auto Wc, auto E) {
+                fs_search_resident_kernel<decltype(NBc)::value, decltype(R)::value, decltype(Wc)::value,
+                                          decltype(E)::value>
+                    <<<s->grid_resident[c], 128, 0, st>>>(s->p, s->d_queues + c,
+                                                          s->d_slots + s->rcls_slot_off[c],
+                                                          s->d_rcls_problems + s->rcls_prob_off[c],
+                                                          s->rcls_count[c]);
+            });
+            s->ctx->launches++;
+            if (s->profiling) {
+                BP_CUDA(cudaEventRecord(s->ev[3 * k + 1], st));
+                BP_CUDA(cudaEventRecord(s->ev[3 * k + 2], st));
+            }
+        }
+        BP_CUDA(cudaGetLastError());
+        if (fork) {
+            for (size_t k = 0; k < s->rclasses.size(); ++k) {
+                BP_CUDA(cudaEventRecord(s->rcls_done[k], s->rcls_stream[k]));
+                BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->rcls_done[k], 0));
+            }
+        }
+        if (s->profiling) s->ev_depths = (int)s->rclasses.size();
+        s->ran_resident = true;
+        s->cur_depth = s->max_depth;
+        return BP_OK;
     }
     if (s->profiling || s->classes.size() == 1 || getenv("BP_SERIAL_CLASSES")) {
         while (s->cur_depth < s->max_depth) {
@@ -1249,7 +1813,34 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
     if (child_scores)
         BP_CUDA(cudaMemcpyAsync(child_scores, p.child_scores, P * (p.es / 2) * p.es * 4,
                                 cudaMemcpyDeviceToHost, st));
+    std::vector<UnitQueue> queues;
+    if (s->ran_resident) {
+        queues.resize(RS_CLASSES);
+        BP_CUDA(cudaMemcpyAsync(queues.data(), s->d_queues, RS_CLASSES * sizeof(UnitQueue),
+                                cudaMemcpyDeviceToHost, st));
+    }
     BP_CUDA(cudaStreamSynchronize(st));
+    for (int c : s->rclasses) {
+        if (!s->ran_resident) break;
+        if (queues[c].abort || queues[c].in_flight != 0) {
+            std::vector<int> pending(P);
+            cudaMemcpy(pending.data(), p.pending, P * 4, cudaMemcpyDeviceToHost);
+            int stuck = -1, n_stuck = 0;
+            for (size_t i = 0; i < P; ++i)
+                if (status[i] == ST_ACTIVE && resident_class_of(s->h_desc[i].cls) == c) {
+                    if (stuck < 0) stuck = (int)i;
+                    n_stuck++;
+                }
+            set_error("resident search kernel of class %d gave up (abort=%d, %d problems in flight): %s; "
+                      "head=%llu tail=%llu est_units=%d init_done=%u; %d active, first: problem %d "
+                      "depth %d pending %d",
+                      c, queues[c].abort, queues[c].in_flight,
+                      queues[c].abort == 2 ? "unit ring overrun" : "a warp waited too long for work",
+                      queues[c].head, queues[c].tail, queues[c].est_units, queues[c].init_done,
+                      n_stuck, stuck, stuck >= 0 ? depth[stuck] : -1, stuck >= 0 ? pending[stuck] : -1);
+            return BP_ERR_STATE;
+        }
+    }
     for (size_t i = 0; i < P; ++i) {
         bp_search_result& r = results[i];
         r.depth = depth[i];
