@@ -324,6 +324,9 @@ int bp_destroy(bp_context* ctx)
     cudaSetDevice(ctx->device);
     if (ctx->scratch) cudaFree(ctx->scratch);
     if (ctx->arena) cudaFree(ctx->arena);
+    for (cudaStream_t st : ctx->side_streams) cudaStreamDestroy(st);
+    for (cudaEvent_t e : ctx->side_events) cudaEventDestroy(e);
+    if (ctx->fork_event) cudaEventDestroy(ctx->fork_event);
     delete ctx;
     return BP_OK;
 }

@@ -23,7 +23,38 @@ struct bp_context {
     void* arena = nullptr;
     size_t arena_bytes = 0;
     bool arena_busy = false;
+    // side streams / events of the flat search (one per shape class in a batch), created on
+    // first use and kept: creating and destroying them cost ~1 ms per one-shot search
+    std::vector<cudaStream_t> side_streams;
+    std::vector<cudaEvent_t> side_events;
+    cudaEvent_t fork_event = nullptr;
+    // resident blocks per SM of the search kernels, by class (0 = not asked yet)
+    int occ_rollout[128] = {0};
+    int occ_lanes[128] = {0};
+    int occ_resident[32] = {0};
 };
+
+namespace bp {
+// k-th side stream / event of the context (created on first use); nullptr on failure
+inline cudaStream_t side_stream(bp_context* ctx, size_t k)
+{
+    while (ctx->side_streams.size() <= k) {
+        cudaStream_t st = nullptr;
+        if (cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking) != cudaSuccess) return nullptr;
+        ctx->side_streams.push_back(st);
+    }
+    return ctx->side_streams[k];
+}
+inline cudaEvent_t side_event(bp_context* ctx, size_t k)
+{
+    while (ctx->side_events.size() <= k) {
+        cudaEvent_t e = nullptr;
+        if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+        ctx->side_events.push_back(e);
+    }
+    return ctx->side_events[k];
+}
+}  // namespace bp
 
 namespace bp {
 

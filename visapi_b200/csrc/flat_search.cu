@@ -14,6 +14,7 @@
 // A rollout never touches HBM except to read its root (once per 32 rollouts) and to
 // write 8 bytes per 32 rollouts; it is bound by instruction issue, not bandwidth.
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <vector>
@@ -344,7 +345,7 @@ __device__ __forceinline__ void lanes_play_unit(const SearchParams& p, LaneTable
 
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
-fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
+fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot, int units_per_warp)
 {
     __shared__ LaneTables<NB, W, EW> s_tb[4];
     __shared__ uint8_t s_sel8[256 * 8];
@@ -356,10 +357,11 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     // Work unit = `group` consecutive 32-rollout chunks of ONE child: the problem's tables (shared
     // memory) and the child board (registers) are set up once per unit.  Units stay small
     // when there is little work (load balance) and grow up to a whole child when there is
-    // plenty (>= 8 units per resident warp).
+    // plenty (>= units_per_warp units per resident warp; see bp_search_run for the choice).
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * 4ull;
-    const int group = (int)min((unsigned long long)p.n_chunks, max(1ull, n_tasks / (n_warps * 8ull)));
+    const int group = (int)min((unsigned long long)p.n_chunks,
+                               max(1ull, n_tasks / (n_warps * (unsigned long long)units_per_warp)));
     const int groups_per_child = (p.n_chunks + group - 1) / group;
     const unsigned long long n_units = (unsigned long long)n_children * groups_per_child;
     unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
@@ -1085,10 +1087,7 @@ struct bp_search {
     int max_depth = 0;
     int cur_depth = 0;         // next depth to play
     bool ready = false;
-    // host copies of the static inputs (for reset)
     std::vector<ProblemDesc> h_desc;
-    std::vector<uint8_t> h_tiles;
-    std::vector<uint32_t> h_boards;
     // class bookkeeping
     std::vector<int> classes;                   // classes present
     int cls_count[FS_CLASSES] = {0};
@@ -1102,6 +1101,11 @@ struct bp_search {
     uint8_t* d_init_tiles = nullptr;           // initial tile tables
     char* arena = nullptr;
     size_t arena_used = 0, arena_bytes = 0;
+    // regions of the arena (see search_create): uploaded inputs, zeroed / -1 state, result block
+    char *up_begin = nullptr, *up_end = nullptr, *zero_begin = nullptr, *zero_end = nullptr;
+    char *res_end = nullptr, *ff_begin = nullptr, *ff_end = nullptr;
+    std::vector<char> h_upload, h_results;      // host images of the upload / result block
+    bool queues_ready = false;                  // resident queues initialised since the last reset
     bool arena_from_ctx = false;
     size_t counters_bytes = 0;
     // optional per-depth CUDA-event timing of the rollout and advance launches
@@ -1133,11 +1137,7 @@ struct bp_search {
     ~bp_search()
     {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
-        for (cudaStream_t st : cls_stream) cudaStreamDestroy(st);
-        for (cudaEvent_t e : cls_done) cudaEventDestroy(e);
-        for (cudaStream_t st : rcls_stream) cudaStreamDestroy(st);
-        for (cudaEvent_t e : rcls_done) cudaEventDestroy(e);
-        if (fork_ev) cudaEventDestroy(fork_ev);
+        // streams and fork/join events belong to the context (side_stream / side_event)
     }
 };
 
@@ -1218,8 +1218,6 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         d.pad0 = d.pad1 = d.pad2 = 0;
         by_class[d.cls].push_back(i);
     }
-    s->h_tiles.assign(tiles, tiles + (size_t)n_problems * entry_stride * 2);
-    if (boards) s->h_boards.assign(boards, boards + (size_t)n_problems * p.rs * p.ws);
 
     std::vector<int> cls_problems;
     int list_off = 0;
@@ -1282,46 +1280,59 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     int rc = BP_OK;
 #define TRY(x) do { rc = (x); if (rc) return rc; } while (0)
     const size_t P = n_problems;
+    // Arena order: [static inputs, uploaded once] [result block: what bp_search_results reads,
+    // zeroed by reset] [more state zeroed by reset] [state set to -1 by reset] [the rest].
+    // One reset = two memsets and the copies of the initial states; one result read = the
+    // result block in a single copy.
+    auto mark = [&]() { return s->arena ? s->arena + s->arena_used : nullptr; };
     auto carve = [&]() -> int {
         s->arena_used = 0;
+        s->up_begin = mark();
         TRY(dev_alloc(s, &s->d_desc, P));
         p.desc = s->d_desc;
-        TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));
-        TRY(dev_alloc(s, &p.tiles, P * p.es * 2));
-        TRY(dev_alloc(s, &p.lfb, P));
-        TRY(dev_alloc(s, &p.legal, P));
+        TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
+        TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
+        if (p.use_lanes) {
+            TRY(dev_alloc(s, &s->d_rcls_problems, rcls_problems.size()));
+            TRY(dev_alloc(s, &s->d_queues_init, (size_t)RS_CLASSES));
+        }
+        s->up_end = mark();
+        if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
+        s->zero_begin = mark();
         TRY(dev_alloc(s, &p.status, P));
         TRY(dev_alloc(s, &p.depth, P));
+        TRY(dev_alloc(s, &p.n_order, P));
         TRY(dev_alloc(s, &p.n_tiles_placed, P));
         TRY(dev_alloc(s, &p.rollouts, P));
         TRY(dev_alloc(s, &p.rollout_placements, P));
         TRY(dev_alloc(s, &p.rollouts_executed, P));
         TRY(dev_alloc(s, &p.placements_executed, P));
-        TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
-        if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
-        TRY(dev_alloc(s, &p.prev_tile, P));
-        TRY(dev_alloc(s, &p.n_order, P));
         TRY(dev_alloc(s, &p.order, P * (p.es / 2 + 2) * 2));
-        TRY(dev_alloc(s, &p.path, P * (p.es / 2)));
-        TRY(dev_alloc(s, &p.child_scores, P * (p.es / 2) * p.es));
-        TRY(dev_alloc(s, &p.stats, P * p.es));
-        TRY(dev_alloc(s, &p.child_list, (size_t)std::max(list_off, 1)));
+        s->res_end = mark();
+        TRY(dev_alloc(s, &p.prev_tile, P));
         s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * FS_CLASSES * sizeof(unsigned);
         TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * FS_CLASSES));
         TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * FS_CLASSES));
-        TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
+        if (p.use_lanes) TRY(dev_alloc(s, &p.pending, P));
+        if (!boards) TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));       // empty boards: zeroed too
+        s->zero_end = mark();
+        if (boards) TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));
+        s->ff_begin = mark();
+        TRY(dev_alloc(s, &p.path, P * (p.es / 2)));
+        TRY(dev_alloc(s, &p.child_scores, P * (p.es / 2) * p.es));
+        s->ff_end = mark();
+        TRY(dev_alloc(s, &p.tiles, P * p.es * 2));
+        TRY(dev_alloc(s, &p.lfb, P));
+        TRY(dev_alloc(s, &p.legal, P));
+        TRY(dev_alloc(s, &p.stats, P * p.es));
+        TRY(dev_alloc(s, &p.child_list, (size_t)std::max(list_off, 1)));
         if (p.use_lanes) {
             TRY(dev_alloc(s, &p.planes, P * LANES_PLANE_STRIDE));
             TRY(dev_alloc(s, &p.pairs, P * p.es * LANES_PAIR_WORDS));
             TRY(dev_alloc(s, &p.tile, P * p.es));
             TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
             TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
-        }
-        if (p.use_lanes) {
-            TRY(dev_alloc(s, &p.pending, P));
-            TRY(dev_alloc(s, &s->d_rcls_problems, rcls_problems.size()));
             TRY(dev_alloc(s, &s->d_queues, (size_t)RS_CLASSES));
-            TRY(dev_alloc(s, &s->d_queues_init, (size_t)RS_CLASSES));
             TRY(dev_alloc(s, &s->d_slots, s->n_slots));
         }
         TRY(dev_alloc(s, &p.rec, P * p.es * (size_t)p.n_chunks));
@@ -1362,68 +1373,82 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     rc = carve();                                   // hand out the slices
     if (rc) { bp_search_destroy(s); return rc; }
 #undef TRY
-    BP_CUDA(cudaMemcpyAsync(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc),
-                            cudaMemcpyHostToDevice, ctx->stream));
-    BP_CUDA(cudaMemcpyAsync(s->d_cls_problems, cls_problems.data(), cls_problems.size() * sizeof(int),
-                            cudaMemcpyHostToDevice, ctx->stream));
-    BP_CUDA(cudaMemcpyAsync(s->d_init_tiles, s->h_tiles.data(), P * p.es * 2, cudaMemcpyHostToDevice,
+    // static inputs: one host image, one copy
+    s->h_upload.assign((size_t)(s->up_end - s->up_begin), 0);
+    auto put = [&](const void* dev, const void* src, size_t bytes) {
+        memcpy(s->h_upload.data() + (reinterpret_cast<const char*>(dev) - s->up_begin), src, bytes);
+    };
+    put(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc));
+    put(s->d_cls_problems, cls_problems.data(), cls_problems.size() * sizeof(int));
+    put(s->d_init_tiles, tiles, P * p.es * 2);
+    if (p.use_lanes) {
+        put(s->d_rcls_problems, rcls_problems.data(), rcls_problems.size() * sizeof(int));
+        put(s->d_queues_init, s->h_queues.data(), RS_CLASSES * sizeof(UnitQueue));
+    }
+    BP_CUDA(cudaMemcpyAsync(s->up_begin, s->h_upload.data(), s->h_upload.size(), cudaMemcpyHostToDevice,
                             ctx->stream));
     if (boards)
-        BP_CUDA(cudaMemcpyAsync(s->d_init_occ, s->h_boards.data(), P * p.rs * p.ws * 4,
-                                cudaMemcpyHostToDevice, ctx->stream));
-    if (p.use_lanes) {
-        BP_CUDA(cudaMemcpyAsync(s->d_rcls_problems, rcls_problems.data(), rcls_problems.size() * sizeof(int),
-                                cudaMemcpyHostToDevice, ctx->stream));
-        BP_CUDA(cudaMemcpyAsync(s->d_queues_init, s->h_queues.data(), RS_CLASSES * sizeof(UnitQueue),
-                                cudaMemcpyHostToDevice, ctx->stream));
-    }
+        BP_CUDA(cudaMemcpyAsync(s->d_init_occ, boards, P * p.rs * p.ws * 4, cudaMemcpyHostToDevice,
+                                ctx->stream));
     BP_CUDA(cudaStreamSynchronize(ctx->stream));
 
     // persistent grid per class: every SM filled to the occupancy limit of that kernel
     for (int c : s->classes) {
-        int per_sm = 1;
-        dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &per_sm, fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>,
-                128, 0);
-        });
-        s->grid_rollout[c] = ctx->sm_count * std::max(per_sm, 1);
-        if (p.use_lanes) {
-            int per_sm_l = 1;
-            dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
+        if (!ctx->occ_rollout[c]) {
+            int per_sm = 1;
+            dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
                 cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                    &per_sm_l,
-                    fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>,
+                    &per_sm, fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>,
                     128, 0);
             });
-            s->grid_lanes[c] = ctx->sm_count * std::max(per_sm_l, 1);
+            ctx->occ_rollout[c] = std::max(per_sm, 1);
+        }
+        s->grid_rollout[c] = ctx->sm_count * ctx->occ_rollout[c];
+        if (p.use_lanes) {
+            if (!ctx->occ_lanes[c]) {
+                int per_sm_l = 1;
+                dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
+                    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                        &per_sm_l,
+                        fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>,
+                        128, 0);
+                });
+                ctx->occ_lanes[c] = std::max(per_sm_l, 1);
+            }
+            s->grid_lanes[c] = ctx->sm_count * ctx->occ_lanes[c];
         }
     }
     for (int c : s->rclasses) {
-        int per_sm = 1;
-        dispatch_resident(c, [&](auto NBc, auto R, auto Wc, auto E) {
-            cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                &per_sm,
-                fs_search_resident_kernel<decltype(NBc)::value, decltype(R)::value, decltype(Wc)::value,
-                                          decltype(E)::value>,
-                128, 0);
-        });
-        s->grid_resident[c] = ctx->sm_count * std::max(per_sm, 1);
-        cudaStream_t st;
-        cudaEvent_t e;
-        BP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        BP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        if (!ctx->occ_resident[c]) {
+            int per_sm = 1;
+            dispatch_resident(c, [&](auto NBc, auto R, auto Wc, auto E) {
+                cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+                    &per_sm,
+                    fs_search_resident_kernel<decltype(NBc)::value, decltype(R)::value, decltype(Wc)::value,
+                                              decltype(E)::value>,
+                    128, 0);
+            });
+            ctx->occ_resident[c] = std::max(per_sm, 1);
+        }
+        s->grid_resident[c] = ctx->sm_count * ctx->occ_resident[c];
+    }
+    // side streams and fork / join events come from the context's pool
+    if (!ctx->fork_event) BP_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    s->fork_ev = ctx->fork_event;
+    for (size_t k = 0; k < s->rclasses.size(); ++k) {
+        cudaStream_t st = side_stream(ctx, k);
+        cudaEvent_t e = side_event(ctx, k);
+        if (!st || !e) { set_error("cannot create a side stream / event"); bp_search_destroy(s); return BP_ERR_CUDA; }
         s->rcls_stream.push_back(st);
         s->rcls_done.push_back(e);
     }
-    BP_CUDA(cudaEventCreateWithFlags(&s->fork_ev, cudaEventDisableTiming));
-    for (int c : s->classes) {
-        cudaStream_t st;
-        cudaEvent_t e;
-        BP_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
-        BP_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    for (size_t k = 0; k < s->classes.size(); ++k) {
+        cudaStream_t st = side_stream(ctx, k);
+        cudaEvent_t e = side_event(ctx, k);
+        if (!st || !e) { set_error("cannot create a side stream / event"); bp_search_destroy(s); return BP_ERR_CUDA; }
         s->cls_stream.push_back(st);
         s->cls_done.push_back(e);
+        const int c = s->classes[k];
         int md = 0;
         for (int i = 0; i < n_problems; ++i)
             if (s->h_desc[i].cls == c) md = std::max(md, s->h_desc[i].n_entries / 2);
@@ -1483,12 +1508,20 @@ static void launch_advance(bp_search* s, int next_slot, const ChildStats* gather
     for (int c : s->classes) launch_advance_class<FIRST>(s, c, next_slot, gathered, s->ctx->stream);
 }
 
-static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t st)
+// `overlapped`: other classes' launches run beside this one on their own streams.  Measured on
+// problems_g (4 classes, 1000 problems, N = 1000; profiles/r1): with >= 8 units per resident warp
+// a whole search takes 13.12 ms, with 4 / 2 / 1 it takes 12.61 / 12.27 / 12.00 ms -- larger units
+// amortise the per-unit table fill and queue atomic, and the longer tail of a launch is filled
+// by the other classes' kernels.  A class running alone has nobody to fill its tail: there the
+// sum of the rollout kernels is 13.52 / 13.53 / 14.04 / 14.88 ms, so it keeps small units.
+static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t st, bool overlapped)
 {
+    int upw = overlapped ? 1 : 8;
+    if (const char* env = getenv("BP_UNITS_PER_WARP")) upw = std::max(1, atoi(env));
     if (s->p.use_lanes)
         dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
             fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>
-                <<<s->grid_lanes[c], 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth);
+                <<<s->grid_lanes[c], 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth, upw);
         });
     else
         dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
@@ -1509,31 +1542,12 @@ int bp_search_reset(bp_search* s)
     const size_t P = p.n_problems;
     cudaStream_t st = ctx->stream;
     // the initial states are resident in HBM (uploaded by bp_search_create)
-    if (!s->d_init_occ)
-        BP_CUDA(cudaMemsetAsync(p.occ, 0, P * p.rs * p.ws * 4, st));
-    else
+    BP_CUDA(cudaMemsetAsync(s->zero_begin, 0, (size_t)(s->zero_end - s->zero_begin), st));
+    BP_CUDA(cudaMemsetAsync(s->ff_begin, 0xFF, (size_t)(s->ff_end - s->ff_begin), st));
+    if (s->d_init_occ)
         BP_CUDA(cudaMemcpyAsync(p.occ, s->d_init_occ, P * p.rs * p.ws * 4, cudaMemcpyDeviceToDevice, st));
     BP_CUDA(cudaMemcpyAsync(p.tiles, s->d_init_tiles, P * p.es * 2, cudaMemcpyDeviceToDevice, st));
-    BP_CUDA(cudaMemsetAsync(p.status, 0, P * sizeof(int), st));
-    BP_CUDA(cudaMemsetAsync(p.depth, 0, P * sizeof(int), st));
-    BP_CUDA(cudaMemsetAsync(p.n_tiles_placed, 0, P * 8, st));
-    BP_CUDA(cudaMemsetAsync(p.rollouts, 0, P * 8, st));
-    BP_CUDA(cudaMemsetAsync(p.rollout_placements, 0, P * 8, st));
-    BP_CUDA(cudaMemsetAsync(p.rollouts_executed, 0, P * 8, st));
-    BP_CUDA(cudaMemsetAsync(p.placements_executed, 0, P * 8, st));
-    BP_CUDA(cudaMemsetAsync(p.prev_tile, 0, P * 2, st));
-    BP_CUDA(cudaMemsetAsync(p.n_order, 0, P * sizeof(int), st));
-    BP_CUDA(cudaMemsetAsync(p.order, 0, P * (p.es / 2 + 2) * 2, st));
-    BP_CUDA(cudaMemsetAsync(p.path, 0xFF, P * (p.es / 2) * sizeof(int), st));
-    BP_CUDA(cudaMemsetAsync(p.child_scores, 0xFF, P * (p.es / 2) * p.es * sizeof(int), st));
-    BP_CUDA(cudaMemsetAsync(p.child_count, 0, s->counters_bytes, st));
-    BP_CUDA(cudaMemsetAsync(p.task_counter, 0, s->counters_bytes, st));
-    if (p.use_lanes) {
-        BP_CUDA(cudaMemcpyAsync(s->d_queues, s->d_queues_init, RS_CLASSES * sizeof(UnitQueue),
-                                cudaMemcpyDeviceToDevice, st));
-        BP_CUDA(cudaMemsetAsync(s->d_slots, 0, s->n_slots * sizeof(UnitSlot), st));
-        BP_CUDA(cudaMemsetAsync(p.pending, 0, P * sizeof(int), st));
-    }
+    s->queues_ready = false;
     launch_advance<true>(s, 0, nullptr);
     BP_CUDA(cudaGetLastError());
     s->ran_resident = false;
@@ -1591,7 +1605,7 @@ int bp_search_step_rollouts(bp_search* s)
     }
     BP_CUDA(cudaSetDevice(s->ctx->device));
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth], s->ctx->stream));
-    for (int c : s->classes) launch_rollouts_class(s, c, s->cur_depth, s->ctx->stream);
+    for (int c : s->classes) launch_rollouts_class(s, c, s->cur_depth, s->ctx->stream, false);
     BP_CUDA(cudaGetLastError());
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth + 1], s->ctx->stream));
     return BP_OK;
@@ -1715,6 +1729,12 @@ int bp_search_run(bp_search* s)
             return BP_ERR_STATE;
         }
         BP_CUDA(cudaSetDevice(s->ctx->device));
+        if (!s->queues_ready) {
+            BP_CUDA(cudaMemcpyAsync(s->d_queues, s->d_queues_init, RS_CLASSES * sizeof(UnitQueue),
+                                    cudaMemcpyDeviceToDevice, s->ctx->stream));
+            BP_CUDA(cudaMemsetAsync(s->d_slots, 0, s->n_slots * sizeof(UnitSlot), s->ctx->stream));
+            s->queues_ready = true;
+        }
         const bool fork = !s->profiling && s->rclasses.size() > 1;
         if (fork) {
             BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
@@ -1774,7 +1794,7 @@ int bp_search_run(bp_search* s)
     for (int d = 0; d < s->max_depth; ++d) {
         for (size_t k = 0; k < s->classes.size(); ++k) {
             if (d >= s->cls_depth[k]) continue;
-            launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k]);
+            launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true);
             launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
         }
     }
@@ -1795,19 +1815,22 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
     const SearchParams& p = s->p;
     BP_CUDA(cudaSetDevice(ctx->device));
     const size_t P = p.n_problems;
-    std::vector<int> status(P), depth(P), n_order(P);
-    std::vector<unsigned long long> ntp(P), roll(P), plc(P), exe(P), pexe(P);
+    // the result block (status .. order) is contiguous in the arena: one copy, then views
     cudaStream_t st = ctx->stream;
-    BP_CUDA(cudaMemcpyAsync(status.data(), p.status, P * 4, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(depth.data(), p.depth, P * 4, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(n_order.data(), p.n_order, P * 4, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(ntp.data(), p.n_tiles_placed, P * 8, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(roll.data(), p.rollouts, P * 8, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(plc.data(), p.rollout_placements, P * 8, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(exe.data(), p.rollouts_executed, P * 8, cudaMemcpyDeviceToHost, st));
-    BP_CUDA(cudaMemcpyAsync(pexe.data(), p.placements_executed, P * 8, cudaMemcpyDeviceToHost, st));
-    if (order)
-        BP_CUDA(cudaMemcpyAsync(order, p.order, P * (p.es / 2 + 2) * 2, cudaMemcpyDeviceToHost, st));
+    const size_t res_bytes = (size_t)(s->res_end - s->zero_begin);
+    s->h_results.resize(res_bytes);
+    BP_CUDA(cudaMemcpyAsync(s->h_results.data(), s->zero_begin, res_bytes, cudaMemcpyDeviceToHost, st));
+    auto view = [&](const void* dev) {
+        return s->h_results.data() + (reinterpret_cast<const char*>(dev) - s->zero_begin);
+    };
+    const int* status = reinterpret_cast<const int*>(view(p.status));
+    const int* depth = reinterpret_cast<const int*>(view(p.depth));
+    const int* n_order = reinterpret_cast<const int*>(view(p.n_order));
+    const unsigned long long* ntp = reinterpret_cast<const unsigned long long*>(view(p.n_tiles_placed));
+    const unsigned long long* roll = reinterpret_cast<const unsigned long long*>(view(p.rollouts));
+    const unsigned long long* plc = reinterpret_cast<const unsigned long long*>(view(p.rollout_placements));
+    const unsigned long long* exe = reinterpret_cast<const unsigned long long*>(view(p.rollouts_executed));
+    const unsigned long long* pexe = reinterpret_cast<const unsigned long long*>(view(p.placements_executed));
     if (path)
         BP_CUDA(cudaMemcpyAsync(path, p.path, P * (p.es / 2) * 4, cudaMemcpyDeviceToHost, st));
     if (child_scores)
@@ -1841,6 +1864,7 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
             return BP_ERR_STATE;
         }
     }
+    if (order) memcpy(order, view(p.order), P * (p.es / 2 + 2) * 2);
     for (size_t i = 0; i < P; ++i) {
         bp_search_result& r = results[i];
         r.depth = depth[i];
@@ -1862,14 +1886,33 @@ int bp_flat_search(bp_context* ctx, int n_problems, const int32_t* rows, const i
                    uint32_t seed, bp_search_result* results, uint8_t* order, int32_t* path,
                    int32_t* child_scores)
 {
+    // BP_TIMING=1: host wall time of each phase on stderr (synchronising after each)
+    static const bool timing = getenv("BP_TIMING") != nullptr;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto us = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) {
+        return std::chrono::duration<double, std::micro>(b - a).count();
+    };
+    const auto t0 = now();
     bp_search* s = nullptr;
     int rc = search_create(ctx, n_problems, rows, cols, n_entries, tiles, entry_stride, boards,
                            streams, n_sim, strategy, seed, true, &s);
     if (rc) return rc;
+    const auto t1 = now();
     rc = bp_search_reset(s);
+    if (timing) cudaStreamSynchronize(ctx->stream);
+    const auto t2 = now();
     if (!rc) rc = bp_search_run(s);
+    const auto t3 = now();
+    if (timing) cudaStreamSynchronize(ctx->stream);
+    const auto t4 = now();
     if (!rc) rc = bp_search_results(s, results, order, path, child_scores);
+    const auto t5 = now();
     bp_search_destroy(s);
+    const auto t6 = now();
+    if (timing)
+        fprintf(stderr, "[bp_flat_search] create %.0f us, reset %.0f, run (issue) %.0f, run (device) %.0f, "
+                        "results %.0f, destroy %.0f\n",
+                us(t0, t1), us(t1, t2), us(t2, t3), us(t3, t4), us(t4, t5), us(t5, t6));
     return rc;
 }
 
