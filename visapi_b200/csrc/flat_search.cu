@@ -1105,6 +1105,7 @@ struct bp_search {
     char *up_begin = nullptr, *up_end = nullptr, *zero_begin = nullptr, *zero_end = nullptr;
     char *res_end = nullptr, *ff_begin = nullptr, *ff_end = nullptr;
     std::vector<char> h_upload, h_results;      // host images of the upload / result block
+    bool in_profiled_run = false;               // bp_search_run is stepping the depths itself
     bool queues_ready = false;                  // resident queues initialised since the last reset
     bool arena_from_ctx = false;
     size_t counters_bytes = 0;
@@ -1605,7 +1606,10 @@ int bp_search_step_rollouts(bp_search* s)
     }
     BP_CUDA(cudaSetDevice(s->ctx->device));
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth], s->ctx->stream));
-    for (int c : s->classes) launch_rollouts_class(s, c, s->cur_depth, s->ctx->stream, false);
+    // (a profiled bp_search_run serialises the classes but keeps the unit size of the real run,
+    // so the per-kernel times and instruction counts describe the kernel that is timed)
+    for (int c : s->classes)
+        launch_rollouts_class(s, c, s->cur_depth, s->ctx->stream, s->in_profiled_run && s->classes.size() > 1);
     BP_CUDA(cudaGetLastError());
     if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * s->cur_depth + 1], s->ctx->stream));
     return BP_OK;
@@ -1772,13 +1776,14 @@ int bp_search_run(bp_search* s)
         return BP_OK;
     }
     if (s->profiling || s->classes.size() == 1 || getenv("BP_SERIAL_CLASSES")) {
-        while (s->cur_depth < s->max_depth) {
-            int rc = bp_search_step_rollouts(s);
-            if (rc) return rc;
-            rc = bp_search_step_commit(s, nullptr);
-            if (rc) return rc;
+        s->in_profiled_run = s->profiling;
+        int rc = BP_OK;
+        while (!rc && s->cur_depth < s->max_depth) {
+            rc = bp_search_step_rollouts(s);
+            if (!rc) rc = bp_search_step_commit(s, nullptr);
         }
-        return BP_OK;
+        s->in_profiled_run = false;
+        return rc;
     }
     if (!s->ready || s->cur_depth != 0) {
         set_error("bp_search_run: call bp_search_reset first");
