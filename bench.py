@@ -75,7 +75,7 @@ MEASURED_LANE_PIPE_PCT = {"issue_active": 73.2, "alu": 62.7, "fma": 28.1, "xu": 
 
 def lane_class_key(rows, cols, n_entries):
     nb = 5 if rows <= 31 else (6 if rows <= 63 else (7 if rows <= 127 else 8))
-    w = 1 if cols <= 32 else (2 if cols <= 64 else 4)
+    w = 1 if cols <= 32 else (2 if cols <= 64 else (3 if cols <= 96 else 4))
     return "%d,%d,%d" % (nb, w, 2 if n_entries <= 64 else 4)
 
 

@@ -26,7 +26,7 @@ def cls_of(p):
 
 def lanes_cls_of(p):
     nb = 5 if p.rows <= 31 else (6 if p.rows <= 63 else (7 if p.rows <= 127 else 8))
-    w = 1 if p.cols <= 32 else (2 if p.cols <= 64 else 4)
+    w = 1 if p.cols <= 32 else (2 if p.cols <= 64 else (3 if p.cols <= 96 else 4))
     ew = 2 if 2 * len(p.tiles) <= 64 else 4
     return "%d,%d,%d" % (nb, w, ew)
 

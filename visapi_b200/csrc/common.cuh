@@ -29,8 +29,8 @@ struct bp_context {
     std::vector<cudaEvent_t> side_events;
     cudaEvent_t fork_event = nullptr;
     // resident blocks per SM of the search kernels, by class (0 = not asked yet)
-    int occ_rollout[128] = {0};
-    int occ_lanes[128] = {0};
+    int occ_rollout[256] = {0};
+    int occ_lanes[256] = {0};
     int occ_resident[32] = {0};
 };
 

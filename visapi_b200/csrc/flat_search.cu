@@ -30,7 +30,9 @@ constexpr int ADV_WARPS = 4;
 constexpr uint32_t NONE_U32 = 0xFFFFFFFFu;
 constexpr int MAX_DEPTHS = BP_MAX_ENTRIES / 2 + 1;
 // search class = (height planes the rows need: 5..8) x (warp shape class RHO, W, EJ)
-constexpr int FS_CLASSES = 4 * N_CLASSES;
+// (+ 4 on the plane index: boards of 65..96 columns, whose lane kernel runs with three words per
+// plane instead of four; the warp-per-board kernels of that class keep W = 4)
+constexpr int FS_CLASSES = 8 * N_CLASSES;
 
 enum Status : int { ST_ACTIVE = 0, ST_SOLVED = 1, ST_DEAD = 2 };
 
@@ -1030,7 +1032,8 @@ using namespace bp;
 template <typename F>
 static void dispatch_lanes(int scls, F&& f)
 {
-    const int cls = scls % N_CLASSES, nb = 5 + scls / N_CLASSES;
+    const int cls = scls % N_CLASSES, nb = 5 + (scls / N_CLASSES) % 4;
+    const bool three_words = scls / N_CLASSES >= 4;
     const int ej = cls % 3, w = (cls / 3) % 3;
     auto with_ew = [&](auto NBc, auto Wc) {
         if (ej <= 1) f(NBc, Wc, IC<2>{}); else f(NBc, Wc, IC<4>{});
@@ -1039,7 +1042,9 @@ static void dispatch_lanes(int scls, F&& f)
         switch (w) {
             case 0: with_ew(NBc, IC<1>{}); break;
             case 1: with_ew(NBc, IC<2>{}); break;
-            default: with_ew(NBc, IC<4>{}); break;
+            default:
+                if (three_words) with_ew(NBc, IC<3>{}); else with_ew(NBc, IC<4>{});
+                break;
         }
     };
     switch (nb) {
@@ -1054,7 +1059,7 @@ static void dispatch_lanes(int scls, F&& f)
 constexpr int RS_CLASSES = 24;
 static int resident_class_of(int scls)
 {
-    const int cls = scls % N_CLASSES, nb = 5 + scls / N_CLASSES;
+    const int cls = scls % N_CLASSES, nb = 5 + (scls / N_CLASSES) % 4;
     const int ej = cls % 3, w = (cls / 3) % 3;
     return ((nb - 5) * 3 + w) * 2 + (ej == 2 ? 1 : 0);
 }
@@ -1214,7 +1219,8 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         ProblemDesc& d = s->h_desc[i];
         d.rows = rows[i]; d.cols = cols[i]; d.n_entries = n_entries[i];
         const int nb = rows[i] <= 31 ? 5 : (rows[i] <= 63 ? 6 : (rows[i] <= 127 ? 7 : 8));
-        d.cls = (nb - 5) * N_CLASSES + shape_class(rows[i], cols[i], n_entries[i]);
+        const int three_words = (cols[i] > 64 && cols[i] <= 96) ? 4 : 0;
+        d.cls = (nb - 5 + three_words) * N_CLASSES + shape_class(rows[i], cols[i], n_entries[i]);
         d.stream = streams ? streams[i] : (uint32_t)i;
         d.pad0 = d.pad1 = d.pad2 = 0;
         by_class[d.cls].push_back(i);

@@ -256,25 +256,20 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         const unsigned long long runmask = c64 & ~(c64 + colbit64);
                         run = __popcll(runmask);
                     } else {
-                        // first non-empty word, then the run may continue through whole words
-                        bool found = false, extending = false;
-#pragma unroll
-                        for (int q = 0; q < W; ++q) {
-                            const uint32_t cq = cand[q];
-                            if (!found) {
-                                if (cq != 0u) {
-                                    found = true;
-                                    const uint32_t colbit = cq & (0u - cq);
-                                    const uint32_t runmask = cq & ~(cq + colbit);
-                                    col = 32 * q + __popc(colbit - 1u);
-                                    run = __popc(runmask);
-                                    extending = (runmask >> 31) != 0u;
-                                }
-                            } else if (extending) {
-                                run += __popc(cq & ~(cq + 1u));        // trailing ones
-                                extending = (cq == 0xFFFFFFFFu);
-                            }
-                        }
+                        // W = 3 or 4: two 64-bit halves; the run of the low half continues into
+                        // the high half when it reaches bit 63
+                        const unsigned long long c_lo =
+                            (unsigned long long)cand[0] | ((unsigned long long)cand[W > 1 ? 1 : 0] << 32);
+                        const unsigned long long c_hi =
+                            (unsigned long long)cand[W > 2 ? 2 : 0] |
+                            (W > 3 ? ((unsigned long long)cand[W > 3 ? 3 : 0] << 32) : 0ull);
+                        const bool in_lo = c_lo != 0ull;
+                        const unsigned long long x = in_lo ? c_lo : c_hi;
+                        const unsigned long long cb = x & (0ull - x);
+                        const unsigned long long runmask = x & ~(x + cb);
+                        col = __popcll(cb - 1ull) + (in_lo ? 0 : 64);
+                        run = __popcll(runmask);
+                        if (in_lo && (runmask >> 63)) run += __popcll(c_hi & ~(c_hi + 1ull));
                     }
                     uint32_t legal[EW], cnt[EW];
                     int k = 0;
