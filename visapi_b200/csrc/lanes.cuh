@@ -244,6 +244,7 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                     uint32_t foot[W];
                     uint32_t colbit1 = 0u;
                     unsigned long long colbit64 = 0ull;
+                    bool in_lo = true;                            // W > 2: colbit64 is in the low half
                     int col = 0, run = 0;
                     if (W == 1) {
                         colbit1 = cand[0] & (0u - cand[0]);
@@ -263,10 +264,11 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                         const unsigned long long c_hi =
                             (unsigned long long)cand[W > 2 ? 2 : 0] |
                             (W > 3 ? ((unsigned long long)cand[W > 3 ? 3 : 0] << 32) : 0ull);
-                        const bool in_lo = c_lo != 0ull;
+                        in_lo = c_lo != 0ull;
                         const unsigned long long x = in_lo ? c_lo : c_hi;
                         const unsigned long long cb = x & (0ull - x);
                         const unsigned long long runmask = x & ~(x + cb);
+                        colbit64 = cb;
                         col = __popcll(cb - 1ull) + (in_lo ? 0 : 64);
                         run = __popcll(runmask);
                         if (in_lo && (runmask >> 63)) run += __popcll(c_hi & ~(c_hi + 1ull));
@@ -319,8 +321,29 @@ __device__ __forceinline__ int lanes_rollout(LaneBoard<NB, W, EW> s, int rows, i
                             foot[W > 1 ? 1 : 0] = (uint32_t)(f >> 32);
                         } else {
                             const int tw = (int)t.w();
+                            if (tw <= 64) {
+                                // footprint = width mask * (one-hot column bit).  The column bit has
+                                // ONE non-zero 32-bit limb pw, so the product is (mask * pw) -- two
+                                // wide multiplies whose halves do not overlap -- moved up by the
+                                // limb's index (0..3) with selects
+                                const uint32_t pw_hi = (uint32_t)(colbit64 >> 32);
+                                const uint32_t pw = (uint32_t)colbit64 | pw_hi;
+                                const unsigned long long p0 = (unsigned long long)t.wm_lo() * pw;
+                                const unsigned long long p1 = (unsigned long long)t.wm_hi() * pw;
+                                const uint32_t q0 = (uint32_t)p0;
+                                const uint32_t q1 = (uint32_t)(p0 >> 32) | (uint32_t)p1;
+                                const uint32_t q2 = (uint32_t)(p1 >> 32);
+                                const bool up1 = pw_hi != 0u;
+                                const uint32_t r0 = up1 ? 0u : q0, r1 = up1 ? q0 : q1;
+                                const uint32_t r2 = up1 ? q1 : q2, r3 = up1 ? q2 : 0u;
+                                foot[0] = in_lo ? r0 : 0u;
+                                foot[W > 1 ? 1 : 0] = in_lo ? r1 : 0u;
+                                foot[W > 2 ? 2 : 0] = in_lo ? r2 : r0;
+                                if (W > 3) foot[W > 3 ? 3 : 0] = in_lo ? r3 : r1;
+                            } else {                              // a tile wider than 64 columns
 #pragma unroll
-                            for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
+                                for (int q = 0; q < W; ++q) foot[q] = word_range(col, col + tw, q);
+                            }
                         }
                         lanes_place(s, foot, inv, inv - th);                    // MCTS.py:175-178
 #pragma unroll
