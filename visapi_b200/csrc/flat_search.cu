@@ -382,43 +382,33 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     }
 }
 
-// tables the lane-per-rollout kernel reads, from the warp-per-board state of one problem
-template <int RHO, int W, int EJ>
+// Tables the lane-per-rollout kernel reads, for the state `s` of one problem that was reached
+// by placing a (ph x pw) tile at row pr, column pc of the previous state (ph == 0: `s` is the
+// initial, empty board).  The lane kernel only runs on boards that start empty, so a board is
+// its skyline and the planes are updated, not rebuilt: the columns under the tile all had height
+// pr (the tile sits on the row-major first free cell) and now have height pr + ph.
+template <bool CG, int RHO, int W, int EJ>
 __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int prob, const ProblemDesc& d,
-                                                  const WarpState<RHO, W, EJ>& s, int n_alive)
+                                                  const WarpState<RHO, W, EJ>& s, int n_alive, int pr,
+                                                  int pc, int ph, int pw)
 {
     const int lane = lane_id();
-    // ---- column heights, bit-sliced (every lane computes the same words) ----------------
-    uint32_t pl[8][W];
-#pragma unroll
-    for (int b = 0; b < 8; ++b)
-#pragma unroll
-        for (int q = 0; q < W; ++q) pl[b][q] = 0u;
-#pragma unroll
-    for (int q = 0; q < W; ++q) {
-        for (int cb = 0; cb < 32; ++cb) {
-            int hgt = 255;                                   // padding column: never free
-            if (32 * q + cb < d.cols) {
-                hgt = d.rows;
-#pragma unroll
-                for (int k = RHO - 1; k >= 0; --k) {
-                    const uint32_t b = __ballot_sync(FULLMASK, (s.occ[k][q] >> cb) & 1u);
-                    if (b != FULLMASK) hgt = 32 * k + ctz32(~b);
-                }
-                hgt = min(hgt, d.rows);
-            }
-#pragma unroll
-            for (int b = 0; b < 8; ++b) pl[b][q] |= (uint32_t)((hgt >> b) & 1) << cb;
+    // ---- column heights, bit-sliced and inverted: lane = plane * 4 + word -----------------
+    {
+        uint32_t* gp = p.planes + (size_t)prob * LANES_PLANE_STRIDE;
+        const int b = lane >> 2, q = lane & 3;
+        uint32_t word;
+        if (ph == 0) {
+            word = word_range(0, d.cols, q);           // height 0 in real columns, padding never free
+        } else {
+            const uint32_t diff = (uint32_t)((255 - pr) ^ (255 - pr - ph));
+            word = ld_state<CG>(gp + lane);
+            if ((diff >> b) & 1u) word ^= word_range(pc, pc + pw, q);
         }
+        gp[lane] = word;
     }
-    uint32_t* gp = p.planes + (size_t)prob * LANES_PLANE_STRIDE;
-#pragma unroll
-    for (int b = 0; b < 8; ++b)
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-            if (lane == b * 4 + q) gp[lane] = (q < W) ? ~pl[b][q < W ? q : 0] : 0u;   // inverted
 
-    // ---- per-entry tile record and the masks of equal / rotated live entries -------------
+    // ---- per-entry tile record -------------------------------------------------------------
     uint4* gt = p.tile + (size_t)prob * p.es;
 #pragma unroll
     for (int j = 0; j < EJ; ++j) {
@@ -429,43 +419,79 @@ __device__ __forceinline__ void write_lane_tables(const SearchParams& p, int pro
             gt[e] = make_uint4(s.ent[j] & 0xFFu, wdt, (uint32_t)wm, (uint32_t)(wm >> 32));
         }
     }
-    uint32_t* gg = p.pairs + (size_t)prob * p.es * LANES_PAIR_WORDS;
-    for (int e = 0; e < n_alive; ++e) {
-        uint32_t mine = s.ent[0];
+
+    // ---- pair masks: entry e leaves with its partner, the entry of the rotated tile with the
+    // same rank inside its group of equal entries (a square pairs with its neighbour: rank ^ 1).
+    // Equal entries are adjacent (host-checked), so a group is a run of the list: B = the
+    // entries that start a run; lane = entry; one warp-uniform pass over the runs tells every
+    // entry where the run of its rotation starts and how long it is.
+    uint32_t B[EJ];
 #pragma unroll
-        for (int j = 1; j < EJ; ++j) mine = ((e >> 5) == j) ? s.ent[j] : mine;
-        const uint32_t v = __shfl_sync(FULLMASK, mine, e & 31);
-        const uint32_t rot = ((v & 0xFFu) << 8) | (v >> 8);
-        // masks of the entries equal to v and to its rotation (same value in every lane)
-        uint32_t gm[4] = {0u, 0u, 0u, 0u}, rm[4] = {0u, 0u, 0u, 0u};
+    for (int j = 0; j < EJ; ++j) {
+        uint32_t pv = __shfl_up_sync(FULLMASK, s.ent[j], 1);
+        const uint32_t last_prev = __shfl_sync(FULLMASK, s.ent[j > 0 ? j - 1 : 0], 31);
+        if (lane == 0) pv = j > 0 ? last_prev : 0u;
+        B[j] = __ballot_sync(FULLMASK, s.ent[j] != 0u && s.ent[j] != pv);
+    }
+    int start[EJ], rfirst[EJ], rcount[EJ];
+    uint32_t rot[EJ];
 #pragma unroll
-        for (int j = 0; j < EJ; ++j) {
-            gm[j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == v);
-            rm[j] = __ballot_sync(FULLMASK, v != 0u && s.ent[j] == rot);
+    for (int j = 0; j < EJ; ++j) {
+        rot[j] = ((s.ent[j] & 0xFFu) << 8) | (s.ent[j] >> 8);
+        rfirst[j] = -1;
+        rcount[j] = 0;
+        int st = -1;                                     // start of this entry's own run
+#pragma unroll
+        for (int jj = EJ - 1; jj >= 0; --jj) {
+            if (jj <= j && st < 0) {
+                const uint32_t m = (jj == j) ? (B[jj] & (FULLMASK >> (31 - lane))) : B[jj];
+                if (m) st = 32 * jj + 31 - __clz(m);
+            }
         }
-        // rank of e inside its group; the partner has the same rank in the rotated group
-        // (a square pairs with its neighbour: rank ^ 1)
-        int rank = 0;
+        start[j] = st;
+    }
+    {
+        int run_start = -1;                              // the run being closed (warp-uniform)
+        uint32_t run_value = 0u;
+        auto close_run = [&](int end) {
+            if (run_start >= 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int lo = 32 * j;
-            if (e >= lo + 32) rank += __popc(gm[j]);
-            else if (e > lo) rank += __popc(gm[j] & ((1u << (e - lo)) - 1u));
-        }
-        const int want = (v == rot) ? (rank ^ 1) : rank;
-        // equal entries are adjacent (host-checked), so the rotated group is one run of bits
-        int rfirst = -1, rcount = 0;
+                for (int j = 0; j < EJ; ++j)
+                    if (s.ent[j] != 0u && rot[j] == run_value) {
+                        rfirst[j] = run_start;
+                        rcount[j] = end - run_start;
+                    }
+            }
+        };
 #pragma unroll
-        for (int j = 3; j >= 0; --j) {
-            if (rm[j]) rfirst = 32 * j + (__ffs(rm[j]) - 1);
-            rcount += __popc(rm[j]);
+        for (int jg = 0; jg < EJ; ++jg) {
+            uint32_t m = B[jg];
+            while (m) {                                  // warp-uniform
+                const int bit = __ffs(m) - 1;
+                m &= m - 1u;
+                const uint32_t v = __shfl_sync(FULLMASK, s.ent[jg], bit);
+                close_run(32 * jg + bit);
+                run_start = 32 * jg + bit;
+                run_value = v;
+            }
         }
-        const int partner = (rfirst >= 0 && want < rcount) ? rfirst + want : -1;
-        uint32_t out = 0u;                                   // lane q holds word q of the pair mask
-        if (lane < 4) {
-            if ((e >> 5) == lane) out |= 1u << (e & 31);
-            if (partner >= 0 && (partner >> 5) == lane) out |= 1u << (partner & 31);
-            gg[e * LANES_PAIR_WORDS + lane] = out;
+        close_run(n_alive);
+    }
+    uint4* gg = reinterpret_cast<uint4*>(p.pairs) + (size_t)prob * p.es;
+#pragma unroll
+    for (int j = 0; j < EJ; ++j) {
+        const int e = lane + 32 * j;
+        if (e < n_alive) {
+            const int rank = e - start[j];
+            const int want = (s.ent[j] == rot[j]) ? (rank ^ 1) : rank;
+            const int partner = (rfirst[j] >= 0 && want < rcount[j]) ? rfirst[j] + want : -1;
+            uint32_t out[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                out[q] = ((e >> 5) == q) ? (1u << (e & 31)) : 0u;
+                if (partner >= 0 && (partner >> 5) == q) out[q] |= 1u << (partner & 31);
+            }
+            gg[e] = make_uint4(out[0], out[1], out[2], out[3]);
         }
     }
 
@@ -657,6 +683,7 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
 
     WarpState<RHO, W, EJ> s;
     int n_alive;
+    int placed_r = 0, placed_c = 0, placed_h = 0, placed_w = 0;      // the committed placement
     if (FIRST) {
         load_board_t<CG>(s, p.occ + (size_t)prob * p.rs * p.ws, d.rows, d.cols, p.ws);
         load_entries_t<CG>(s, p.tiles + (size_t)prob * p.es * 2, d.n_entries);
@@ -741,6 +768,7 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
 
         place(s, lfb.x, lfb.y, (int)(v & 0xFFu), (int)(v >> 8));
         kill_pair(s, v);
+        placed_r = lfb.x; placed_c = lfb.y; placed_h = (int)(v & 0xFFu); placed_w = (int)(v >> 8);
 
         if (first_child >= 0) {
             // ---- solved inside a rollout (MCTS.py:77-93) -------------------------
@@ -823,7 +851,7 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
                 base += __popc(legal[j]);
             }
         }
-        if (p.use_lanes) write_lane_tables(p, prob, d, s, n_alive);
+        if (p.use_lanes) write_lane_tables<CG>(p, prob, d, s, n_alive, placed_r, placed_c, placed_h, placed_w);
         if (RESIDENT) publish_units<EJ>(p, q, slots, prob, legal, k, cbuf, n_warps);
     }
     return status;
