@@ -1,6 +1,8 @@
-"""Debug driver of the resident search kernel: runs problem subsets under knob combinations.
+"""The launch-per-depth search against the resident (single-launch) search kernel on several
+workloads: wall time per search, equality of the results, and where the resident kernel's warps
+spent their time (profiles/r1/resident_vs_stepped.txt).
 
-    python tools/debug_resident.py
+    python tools/compare_search_modes.py
 """
 import os
 import sys
@@ -11,9 +13,8 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 
-def run(eng, probs, n_sim, flags, label, reps=2):
+def run(eng, probs, n_sim, label, reps=3):
     from visapi_b200 import datasets
-    os.environ["BP_RESIDENT_FLAGS"] = str(flags)
     batch = datasets.batch_arrays(probs)
     s = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim, 0, 123)
     out = None
@@ -31,15 +32,15 @@ def run(eng, probs, n_sim, flags, label, reps=2):
             if out is None:
                 out = res
             same = all(np.array_equal(res[k], out[k]) for k in ("depth", "solution_found", "rollouts", "order"))
-            print("%-28s flags=%d %-8s %8.2f ms  solved %d  same=%s" %
-                  (label, flags, mode, dt * 1e3, int(res["solution_found"].sum()), same), flush=True)
+            print("%-28s %-8s %8.2f ms  solved %d  same=%s" %
+                  (label, mode, dt * 1e3, int(res["solution_found"].sum()), same), flush=True)
             if mode == "resident":
                 st = s.resident_stats()
                 print("      wait %.3f play %.3f advance %.3f other %.3f  units %d advances %d tickets %d" %
                       (st["wait_frac"], st["play_frac"], st["advance_frac"], st["other_frac"],
                        st["units_played"], st["advances"], st["tickets"]), flush=True)
     except Exception as e:   # noqa: BLE001
-        print("%-28s flags=%d FAILED: %s" % (label, flags, e), flush=True)
+        print("%-28s FAILED: %s" % (label, e), flush=True)
     s.close()
 
 
@@ -50,12 +51,12 @@ def main():
     g = datasets.load_problem_set("g")
     small = [p for p in g if p.rows <= 31 and p.cols <= 32]
     print("class (5,1): %d problems" % len(small), flush=True)
-    for flags in (1, 0):
-        run(eng, small, 1000, flags, "all of class 5,1", reps=3)
-        run(eng, g[:1000], 1000, flags, "g[0:1000]", reps=3)
-    run(eng, g[:1000], 100, 0, "g[0:1000] N=100", reps=3)
-    run(eng, g[:125], 1000, 0, "g[0:125] (1/8 shard)", reps=3)
-    run(eng, g[:1], 1000, 0, "g[0:1]", reps=3)
+    run(eng, small, 1000, "all of class 5,1")
+    run(eng, g[:1000], 1000, "g[0:1000]")
+    run(eng, g[:1000], 100, "g[0:1000] N=100")
+    run(eng, datasets.load_problem_set("b")[:1000], 1000, "b[0:1000]")
+    run(eng, g[:125], 1000, "g[0:125] (1/8 shard)")
+    run(eng, g[:1], 1000, "g[0:1]")
     eng.close()
 
 

@@ -16,7 +16,9 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(HERE, "librectpack_b200.so")
 SOURCES = ["api_basic.cu", "flat_search.cu", "puct.cu"]
-HEADERS = ["board.cuh", "philox.cuh", "common.cuh", os.path.join("..", "..", "include", "rectpack_b200.h")]
+HEADERS = ["board.cuh", "philox.cuh", "common.cuh", "lanes.cuh", "search_types.cuh", "search_queue.cuh",
+           "search_kernels.cuh", "search_resident.cuh",
+           os.path.join("..", "..", "include", "rectpack_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
@@ -49,7 +51,7 @@ def source_hash():
     rebuilt when this changes, not when file times do — a snapshot copied to the GPU box keeps
     its prebuilt .so even if the copy reset the mtimes."""
     h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
-    for name in sorted(_sources()) + sorted(HEADERS + ["lanes.cuh"]):
+    for name in sorted(_sources()) + sorted(HEADERS):
         path = os.path.join(CSRC, name)
         if os.path.exists(path):
             with open(path, "rb") as f:
