@@ -173,7 +173,7 @@ __device__ __forceinline__ void lanes_play_unit(const SearchParams& p, LaneTable
 
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
-fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot, int units_per_warp)
+fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot, int half_units_per_warp)
 {
     __shared__ LaneTables<NB, W, EW> s_tb[4];
     __shared__ uint8_t s_sel8[256 * 8];
@@ -185,11 +185,11 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     // Work unit = `group` consecutive 32-rollout chunks of ONE child: the problem's tables (shared
     // memory) and the child board (registers) are set up once per unit.  Units stay small
     // when there is little work (load balance) and grow up to a whole child when there is
-    // plenty (>= units_per_warp units per resident warp; see bp_search_run for the choice).
+    // plenty (>= half_units_per_warp / 2 units per resident warp; launch_rollouts_class chooses).
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
     const unsigned long long n_warps = (unsigned long long)gridDim.x * 4ull;
     const int group = (int)min((unsigned long long)p.n_chunks,
-                               max(1ull, n_tasks / (n_warps * (unsigned long long)units_per_warp)));
+                               max(1ull, 2ull * n_tasks / (n_warps * (unsigned long long)half_units_per_warp)));
     const int groups_per_child = (p.n_chunks + group - 1) / group;
     const unsigned long long n_units = (unsigned long long)n_children * groups_per_child;
     unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
