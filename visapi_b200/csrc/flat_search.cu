@@ -243,16 +243,21 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     // BP_ROLLOUT=warp forces the warp-per-board kernel
     bool lanes_ok = boards == nullptr;
     if (const char* env = getenv("BP_ROLLOUT")) lanes_ok = lanes_ok && strcmp(env, "warp") != 0;
-    for (int i = 0; i < n_problems && lanes_ok; ++i) {       // equal tiles adjacent in the list?
-        const uint8_t* t = tiles + (size_t)i * entry_stride * 2;
-        std::vector<int> closed;
-        int prev = -1;
-        for (int e = 0; e < n_entries[i]; ++e) {
-            const int v = t[2 * e] | (t[2 * e + 1] << 8);
-            if (v == 0 || v == prev) continue;
-            if (std::find(closed.begin(), closed.end(), v) != closed.end()) { lanes_ok = false; break; }
-            if (prev >= 0) closed.push_back(prev);
-            prev = v;
+    {   // equal tiles adjacent in the list?  closed_in[v] = generation of the problem in which the
+        // run of value v has ended; meeting v again in the same problem breaks the rule
+        static thread_local std::vector<uint32_t> closed_in(1u << 16, 0u);
+        static thread_local uint32_t generation = 0;
+        for (int i = 0; i < n_problems && lanes_ok; ++i) {
+            if (++generation == 0u) { std::fill(closed_in.begin(), closed_in.end(), 0u); generation = 1; }
+            const uint8_t* t = tiles + (size_t)i * entry_stride * 2;
+            int prev = -1;
+            for (int e = 0; e < n_entries[i]; ++e) {
+                const int v = t[2 * e] | (t[2 * e + 1] << 8);
+                if (v == 0 || v == prev) continue;
+                if (closed_in[v] == generation) { lanes_ok = false; break; }
+                if (prev >= 0) closed_in[prev] = generation;
+                prev = v;
+            }
         }
     }
     p.use_lanes = lanes_ok ? 1 : 0;
