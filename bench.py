@@ -18,8 +18,10 @@ value   = rollouts the reference would have made for the same job (its early exi
 e2e     = same metric through the one-shot C-ABI call bp_flat_search with host numpy
           buffers (allocation, H2D, all depths, D2H inside the timed region).
 roofline: the rollout kernel is bound by instruction issue, not by HBM or tensor
-          cores: achieved = placements executed x A(class) / rollout-kernel
-          time, peak = SMs x 4 schedulers x max SM clock.
+          cores: achieved = placements executed x A(class) / step time of the
+          timed region (the class launches overlap, so this bounds the rollout kernels'
+          rate from below; the serialised profiling pass is reported beside it),
+          peak = SMs x 4 schedulers x max SM clock.
 """
 import argparse
 import json
