@@ -133,8 +133,10 @@ def reference_arm(a):
         return
     samples = []
     base = None
+    # bounded sample per step so that the whole run ends within a few minutes for any K
+    budget = min(a.ref_budget, max(2.0, 150.0 / max(a.steps, 1)))
     for i in range(a.warmup + a.steps):
-        base = run_cpu_baseline(a, a.ref_budget if i >= a.warmup else min(a.ref_budget, 2.0),
+        base = run_cpu_baseline(a, budget if i >= a.warmup else min(budget, 2.0),
                                 c_problems=8 if i == a.warmup + a.steps - 1 else 0)
         if i >= a.warmup:
             samples.append(base["python_port"])
@@ -143,7 +145,7 @@ def reference_arm(a):
     value = rollouts / seconds
     cores = samples[-1]["cores"]
     sample = ("python/numpy restatement of reference CustomMCTS.predict, %d single-threaded "
-              "processes, problems in order, %.0f s wall budget per step" % (cores, a.ref_budget))
+              "processes, problems in order, %.1f s wall budget per step" % (cores, budget))
     line = {
         "impl": "reference", "metric": "mcts_rollouts_per_s", "value": value, "unit": "rollouts/s",
         "n_gpus": a.gpus, "steps": a.steps, "warmup": a.warmup,
