@@ -219,7 +219,11 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         d.rows = rows[i]; d.cols = cols[i]; d.n_entries = n_entries[i];
         const int nb = rows[i] <= 31 ? 5 : (rows[i] <= 63 ? 6 : (rows[i] <= 127 ? 7 : 8));
         const int three_words = (cols[i] > 64 && cols[i] <= 96) ? 4 : 0;
-        d.cls = (nb - 5 + three_words) * N_CLASSES + shape_class(rows[i], cols[i], n_entries[i]);
+        // rows per lane of the warp-per-board kernels follow the plane count (31 / 63 / 128 rows),
+        // not ceil(rows / 32): boards of exactly 32 or 64 rows would otherwise form classes of
+        // their own, each with its own chain of launches
+        const int rows_of_class = nb == 5 ? 32 : (nb == 6 ? 64 : 128);
+        d.cls = (nb - 5 + three_words) * N_CLASSES + shape_class(rows_of_class, cols[i], n_entries[i]);
         d.stream = streams ? streams[i] : (uint32_t)i;
         d.pad0 = d.pad1 = d.pad2 = 0;
         by_class[d.cls].push_back(i);
