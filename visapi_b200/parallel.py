@@ -30,7 +30,7 @@ def split_sims(n_sim, rank, world):
 
 def merge_child_stats(per_rank):
     """Host statement of the merge rule the commit kernel applies to the gathered
-    statistics (visapi_b200/csrc/flat_search.cu: stats_from_gathered).  per_rank: array
+    statistics (visapi_b200/csrc/search_kernels.cuh: stats_from_gathered).  per_rank: array
     [world, ...] of CHILD_STATS_DTYPE, rank-major, ranks holding ascending sim ranges."""
     per_rank = np.asarray(per_rank)
     out = np.zeros(per_rank.shape[1:], CHILD_STATS_DTYPE)
