@@ -315,6 +315,11 @@ def test_search_reset_is_repeatable(eng, golden):
         else:
             assert s.last_run_resident()
             assert launches == 1 and rollout_ms > 0 and advance_ms == 0
+            st = s.resident_stats()          # every published unit was played exactly once
+            assert st["units_played"] == st["units_published"] > 0
+            assert st["tickets"] >= st["units_played"] and st["advances"] > 0
+            assert abs(st["wait_frac"] + st["play_frac"] + st["advance_frac"] + st["other_frac"] - 1.0) < 1e-6
+            assert st["play_frac"] > 0 and st["wait_frac"] >= 0
     for o in outs:
         _check_flat(c, o, 0, c["n_sim"], c["strategy"])
     s.close()
