@@ -152,21 +152,22 @@ int bp_search_reset(bp_search *s);
 /* How bp_search_run plays the search (results are identical either way):
  *   BP_SEARCH_STEPPED   one rollout launch + one advance launch per depth and shape class, each
  *                       class's depth loop on its own stream (the form the stepwise API uses);
- *   BP_SEARCH_RESIDENT  ONE launch per shape class runs every depth of every problem: persistent
- *                       warps take work units from a device queue, and the warp that finishes a
- *                       problem's last rollout of a depth scores its children, commits the best
- *                       one (CustomMCTS.predict, binpack/MCTS.py:95-119) and queues the next
- *                       depth's rollouts, so problems advance independently.  Needs the lane
- *                       kernel (see bp_search_info);
- *   BP_SEARCH_AUTO      the faster of the two as measured on B200: STEPPED.
+ *   BP_SEARCH_RESIDENT  ONE launch runs every depth of every problem, all shape classes
+ *                       together: persistent warps take work units from a device queue, and the
+ *                       warp that finishes a problem's last rollout of a depth scores its
+ *                       children, commits the best one (CustomMCTS.predict,
+ *                       binpack/MCTS.py:95-119) and queues the next depth's rollouts, so problems
+ *                       advance independently.  Needs the lane kernel (see bp_search_info) and
+ *                       fewer than 2^20 problems; the only form that runs a partitioned
+ *                       (root-parallel) search without a host step per move;
+ *   BP_SEARCH_AUTO      the faster of the two as measured on B200.
  * The environment variable BP_SEARCH=stepped|resident overrides the mode. */
 typedef enum { BP_SEARCH_AUTO = 0, BP_SEARCH_STEPPED = 1, BP_SEARCH_RESIDENT = 2 } bp_search_mode;
 int bp_search_set_mode(bp_search *s, int mode);
 /* on != 0: time the launches of the next run with CUDA events on the context's stream, shape
  * classes serialised.  bp_search_profile synchronises and returns, for the last run,
  *   stepped:  milliseconds in the rollout kernels / in the advance kernels, over n_depths depths;
- *   resident: milliseconds in the resident kernels (rollout_ms; advance_ms = 0), n_depths = the
- *             number of launches (one per class). */
+ *   resident: milliseconds in the resident kernel (rollout_ms; advance_ms = 0), n_depths = 1. */
 int bp_search_set_profiling(bp_search *s, int on);
 int bp_search_profile(bp_search *s, double *rollout_ms, double *advance_ms, int *n_depths);
 /* run every depth; asynchronous; single rank only.  Each shape class runs on an internal
@@ -182,6 +183,21 @@ int bp_search_run(bp_search *s);
 int bp_search_step_rollouts(bp_search *s);
 int bp_search_step_reduce(bp_search *s);
 int bp_search_step_commit(bp_search *s, const void *gathered_stats_dev);
+/* resident form of the root-parallel search (no host step per move): after
+ * bp_search_set_partition every rank creates its exchange buffer, the ranks swap the 64-byte
+ * CUDA IPC handles (ranks in other processes; ipc_handles = uint8[n_ranks][64] in rank order) or
+ * the raw pointers (ranks of one process; local_ptrs[n_ranks]) and connect; then
+ * bp_search_reset + bp_search_run in BP_SEARCH_RESIDENT mode on every rank, concurrently.
+ * Inside the kernel the warp that finishes a problem's depth stores this rank's per-child
+ * statistics into every rank's buffer over NVLink peer memory, raises a flag there and waits
+ * for the other ranks' flags: the merge of binpack/MCTS.py:126-149 split over GPUs.
+ * All ranks must reset / run the same number of times; synchronise the ranks (host barrier)
+ * before destroying a connected search. */
+int bp_search_exchange_create(bp_search *s, void *ipc_handle_64, void **local_ptr);
+int bp_search_exchange_connect(bp_search *s, const void *ipc_handles, void *const *local_ptrs);
+/* resident kernel blocks per SM (0 = as many as fit): lets several searches be resident on one
+ * device at once (ranks emulated on one GPU wait for each other inside their kernels) */
+int bp_search_set_resident_blocks(bp_search *s, int blocks_per_sm);
 int bp_search_stats_buffer(bp_search *s, void **stats_dev, int64_t *n_bytes);
 int bp_search_max_depth(bp_search *s, int *max_depth);
 /* lane_kernel = 1: rollouts run in the lane-per-rollout kernel (32 rollouts per warp, needs
@@ -191,10 +207,11 @@ int bp_search_max_depth(bp_search *s, int *max_depth);
 int bp_search_info(bp_search *s, int *lane_kernel, int *n_classes);
 /* resident = 1 when the last bp_search_run used the resident kernel */
 int bp_search_last_run(bp_search *s, int *resident);
-/* Where the warps of the last resident run spent their time; synchronises.  out8 = SM clock
+/* Where the warps of the last resident run spent their time; synchronises.  out10 = SM clock
  * cycles summed over all warps: {resident, waiting for a unit, playing units, advancing
- * problems}, then {units played, problems advanced, tickets taken, units published}. */
-int bp_search_resident_stats(bp_search *s, double *out8);
+ * problems}, then {units played, problems advanced, polls of an empty slot}, cycles spent in
+ * the peer-memory exchange (root-parallel), units published, warps launched. */
+int bp_search_resident_stats(bp_search *s, double *out10);
 /* synchronises the stream and copies results to the host
  *   results      : bp_search_result[n_problems]
  *   order        : NULL or uint8[n_problems][entry_stride / 2 + 2][2]  solution_tiles_order

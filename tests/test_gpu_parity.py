@@ -295,6 +295,54 @@ def test_root_parallel_emulated_ranks(eng, golden):
             s.close()
 
 
+def test_root_parallel_resident_exchange_emulated_ranks(golden):
+    """The resident form of the root-parallel search: three 'ranks' = three partitioned searches
+    resident on ONE device at the same time (each on its own stream, a third of the SM slots
+    each), exchanging their per-child statistics through each other's buffers from inside their
+    kernels (the same stores and flags that cross NVLink between real ranks).  Results must be
+    bit-identical to the single-rank search, run after run."""
+    import visapi_b200
+    from visapi_b200 import pack_tiles
+    from visapi_b200.parallel import split_sims
+    import torch
+    cases = [c for c in golden("flat_search.json") if c["n_sim"] in (11, 70) and
+             c["strategy"] == "max_depth"][:4] + \
+            [c for c in golden("flat_search.json") if c["strategy"] == "avg_depth" and c["n_sim"] == 45][:2]
+    world = 3
+    streams = [torch.cuda.Stream() for _ in range(world)]
+    engines = [visapi_b200.Engine(0, stream=st.cuda_stream) for st in streams]
+    try:
+        for c in cases:
+            n_sim, strat = c["n_sim"], 0 if c["strategy"] == "max_depth" else 1
+            args = ([c["rows"]], [c["cols"]], pack_tiles([c["tiles"]]), [len(c["tiles"])], n_sim, strat,
+                    123, [c["stream"]])
+            searches = [e.search(*args) for e in engines]
+            ptrs = []
+            for r, s in enumerate(searches):
+                b, n = split_sims(n_sim, r, world)
+                s.set_partition(r, world, b, n)
+                s.set_mode("resident")
+                s.set_resident_blocks(2)
+                ptrs.append(s.exchange_create()[1])
+            for s in searches:
+                s.exchange_connect(local_ptrs=ptrs)
+            for _ in range(3):                       # flags and buffers carry over between runs
+                for s in searches:
+                    s.reset()
+                for s in searches:
+                    s.run()
+                for s in searches:
+                    res = s.results(want_scores=True)
+                    assert s.last_run_resident()
+                    _check_flat(c, res, 0, n_sim, c["strategy"])
+            torch.cuda.synchronize()
+            for s in searches:
+                s.close()
+    finally:
+        for e in engines:
+            e.close()
+
+
 def test_search_reset_is_repeatable(eng, golden):
     from visapi_b200 import pack_tiles
     c = golden("flat_search.json")[0]
@@ -317,7 +365,7 @@ def test_search_reset_is_repeatable(eng, golden):
             assert launches == 1 and rollout_ms > 0 and advance_ms == 0
             st = s.resident_stats()          # every published unit was played exactly once
             assert st["units_played"] == st["units_published"] > 0
-            assert st["tickets"] >= st["units_played"] and st["advances"] > 0
+            assert st["polls"] >= 0 and st["advances"] > 0
             assert abs(st["wait_frac"] + st["play_frac"] + st["advance_frac"] + st["other_frac"] - 1.0) < 1e-6
             assert st["play_frac"] > 0 and st["wait_frac"] >= 0
     for o in outs:

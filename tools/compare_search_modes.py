@@ -36,9 +36,9 @@ def run(eng, probs, n_sim, label, reps=3):
                   (label, mode, dt * 1e3, int(res["solution_found"].sum()), same), flush=True)
             if mode == "resident":
                 st = s.resident_stats()
-                print("      wait %.3f play %.3f advance %.3f other %.3f  units %d advances %d tickets %d" %
+                print("      wait %.3f play %.3f advance %.3f other %.3f  units %d advances %d polls %d" %
                       (st["wait_frac"], st["play_frac"], st["advance_frac"], st["other_frac"],
-                       st["units_played"], st["advances"], st["tickets"]), flush=True)
+                       st["units_played"], st["advances"], st["polls"]), flush=True)
     except Exception as e:   # noqa: BLE001
         print("%-28s FAILED: %s" % (label, e), flush=True)
     s.close()

@@ -69,6 +69,9 @@ SYMBOLS = [
     ("bp_search_step_commit", C.c_int, [_vp, _vp]),
     ("bp_search_stats_buffer", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
     ("bp_search_max_depth", C.c_int, [_vp, C.POINTER(C.c_int)]),
+    ("bp_search_exchange_create", C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    ("bp_search_exchange_connect", C.c_int, [_vp, _vp, C.POINTER(_vp)]),
+    ("bp_search_set_resident_blocks", C.c_int, [_vp, C.c_int]),
     ("bp_search_info", C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     ("bp_search_last_run", C.c_int, [_vp, C.POINTER(C.c_int)]),
     ("bp_search_resident_stats", C.c_int, [_vp, C.POINTER(C.c_double)]),
@@ -394,13 +397,14 @@ class Search(object):
 
     def resident_stats(self):
         """Time split of the warps of the last resident run (see bp_search_resident_stats)."""
-        out = (C.c_double * 8)()
+        out = (C.c_double * 10)()
         self.engine._check(self._lib.bp_search_resident_stats(self._h, out))
         tot = max(out[0], 1.0)
         return {"warp_cycles": out[0], "wait_frac": out[1] / tot, "play_frac": out[2] / tot,
-                "advance_frac": out[3] / tot, "other_frac": (out[0] - out[1] - out[2] - out[3]) / tot,
-                "units_played": int(out[4]), "advances": int(out[5]), "tickets": int(out[6]),
-                "units_published": int(out[7])}
+                "advance_frac": out[3] / tot, "exchange_frac": out[7] / tot,
+                "other_frac": (out[0] - out[1] - out[2] - out[3] - out[7]) / tot,
+                "units_played": int(out[4]), "advances": int(out[5]), "polls": int(out[6]),
+                "units_published": int(out[8]), "warps": int(out[9])}
 
     def set_profiling(self, on=True):
         self.engine._check(self._lib.bp_search_set_profiling(self._h, int(bool(on))))
@@ -430,6 +434,27 @@ class Search(object):
         ptr, nbytes = C.c_void_p(), C.c_int64()
         self.engine._check(self._lib.bp_search_stats_buffer(self._h, C.byref(ptr), C.byref(nbytes)))
         return ptr.value, nbytes.value
+
+    def exchange_create(self):
+        """Exchange buffer of a partitioned resident search: (64-byte CUDA IPC handle, device
+        pointer).  See bp_search_exchange_create."""
+        handle = np.zeros(64, np.uint8)
+        ptr = C.c_void_p()
+        self.engine._check(self._lib.bp_search_exchange_create(self._h, _ptr(handle), C.byref(ptr)))
+        return handle, ptr.value
+
+    def exchange_connect(self, ipc_handles=None, local_ptrs=None):
+        """ipc_handles: uint8[n_ranks][64] in rank order (ranks in other processes), or local_ptrs:
+        the exchange pointers of the ranks of this process."""
+        if ipc_handles is not None:
+            handles = np.ascontiguousarray(ipc_handles, dtype=np.uint8)
+            self.engine._check(self._lib.bp_search_exchange_connect(self._h, _ptr(handles), None))
+        else:
+            arr = (C.c_void_p * len(local_ptrs))(*[C.c_void_p(int(v)) for v in local_ptrs])
+            self.engine._check(self._lib.bp_search_exchange_connect(self._h, None, arr))
+
+    def set_resident_blocks(self, blocks_per_sm):
+        self.engine._check(self._lib.bp_search_set_resident_blocks(self._h, int(blocks_per_sm)))
 
     def results(self, want_scores=False):
         res = (SearchResult * self.P)()

@@ -15,9 +15,10 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ_DIR = os.path.join(CSRC, "build")
 LIB_PATH = os.path.join(HERE, "librectpack_b200.so")
-SOURCES = ["api_basic.cu", "flat_search.cu", "puct.cu"]
+SOURCES = ["api_basic.cu", "flat_search.cu", "puct.cu", "resident_k22.cu", "resident_k24.cu", "resident_k42.cu",
+           "resident_k44.cu"]
 HEADERS = ["board.cuh", "philox.cuh", "common.cuh", "lanes.cuh", "search_types.cuh", "search_queue.cuh",
-           "search_kernels.cuh", "search_resident.cuh",
+           "search_kernels.cuh", "search_resident.cuh", "resident_variant.cuh",
            os.path.join("..", "..", "include", "rectpack_b200.h")]
 
 NVCC_FLAGS = [

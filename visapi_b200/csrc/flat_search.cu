@@ -20,7 +20,7 @@
 #include <vector>
 
 #include "search_kernels.cuh"
-#include "search_resident.cuh"
+#include "resident_variant.cuh"
 #include "search_types.cuh"
 
 // ================================================================= host side
@@ -54,34 +54,15 @@ static void dispatch_lanes(int scls, F&& f)
     }
 }
 
-// resident-kernel instantiation of a resident class index: ((nb - 5) * 3 + w index) * 2 + (EW == 4)
-constexpr int RS_CLASSES = 24;
-static int resident_class_of(int scls)
-{
-    const int cls = scls % N_CLASSES, nb = 5 + (scls / N_CLASSES) % 4;
-    const int ej = cls % 3, w = (cls / 3) % 3;
-    return ((nb - 5) * 3 + w) * 2 + (ej == 2 ? 1 : 0);
-}
-// f(IC<NB>, IC<RHO>, IC<W>, IC<EJ>)
+// resident-kernel variant: 0 = <2,2>, 1 = <2,4>, 2 = <4,2>, 3 = <4,4> (widest plane words, entry-mask words)
 template <typename F>
-static void dispatch_resident(int rcls, F&& f)
+static void dispatch_resident(int variant, F&& f)
 {
-    const int ew = rcls % 2, w = (rcls / 2) % 3, nb = 5 + rcls / 6;
-    auto with_ew = [&](auto NBc, auto R, auto Wc) {
-        if (ew == 0) f(NBc, R, Wc, IC<2>{}); else f(NBc, R, Wc, IC<4>{});
-    };
-    auto with_w = [&](auto NBc, auto R) {
-        switch (w) {
-            case 0: with_ew(NBc, R, IC<1>{}); break;
-            case 1: with_ew(NBc, R, IC<2>{}); break;
-            default: with_ew(NBc, R, IC<4>{}); break;
-        }
-    };
-    switch (nb) {
-        case 5: with_w(IC<5>{}, IC<1>{}); break;
-        case 6: with_w(IC<6>{}, IC<2>{}); break;
-        case 7: with_w(IC<7>{}, IC<4>{}); break;
-        default: with_w(IC<8>{}, IC<4>{}); break;
+    switch (variant) {
+        case 0: f(IC<2>{}, IC<2>{}); break;
+        case 1: f(IC<2>{}, IC<4>{}); break;
+        case 2: f(IC<4>{}, IC<2>{}); break;
+        default: f(IC<4>{}, IC<4>{}); break;
     }
 }
 
@@ -110,7 +91,6 @@ struct bp_search {
     char *res_end = nullptr, *ff_begin = nullptr, *ff_end = nullptr;
     std::vector<char> h_upload, h_results;      // host images of the upload / result block
     bool in_profiled_run = false;               // bp_search_run is stepping the depths itself
-    bool queues_ready = false;                  // resident queues initialised since the last reset
     bool arena_from_ctx = false;
     size_t counters_bytes = 0;
     // optional per-depth CUDA-event timing of the rollout and advance launches
@@ -123,22 +103,21 @@ struct bp_search {
     std::vector<cudaEvent_t> cls_done;
     std::vector<int> cls_depth;
     cudaEvent_t fork_ev = nullptr;
-    // resident search (one launch per resident class): queues, rings, problem lists
+    // resident search (one launch runs every depth of every problem): queue, ring, variant
     int mode = BP_SEARCH_AUTO;
     bool ran_resident = false;
-    std::vector<int> rclasses;                  // resident classes present
-    int rcls_count[RS_CLASSES] = {0};
-    int rcls_prob_off[RS_CLASSES] = {0};
-    size_t rcls_slot_off[RS_CLASSES] = {0};
-    int grid_resident[RS_CLASSES] = {0};
-    std::vector<UnitQueue> h_queues;            // initial queue headers
-    int* d_rcls_problems = nullptr;
-    UnitQueue* d_queues = nullptr;              // [RS_CLASSES]
-    UnitQueue* d_queues_init = nullptr;
-    UnitSlot* d_slots = nullptr;
-    size_t n_slots = 0;
-    std::vector<cudaStream_t> rcls_stream;
-    std::vector<cudaEvent_t> rcls_done;
+    bool seeded = false;                        // depth 0 is on the queue
+    bool queue_dirty = true;                    // ring / tickets must be cleared before the next run
+    ResidentParams x{};
+    int variant = 0;
+    int grid_resident = 0;
+    size_t ring_cap = 0;
+    UnitQueue h_queue{};                        // header as read back by bp_search_results
+    // root-parallel exchange over peer memory (resident search with n_ranks > 1)
+    void* d_exchange = nullptr;                 // own buffer: gathered[4][R][P][ES] + arrived[P][8]
+    size_t exchange_bytes = 0, exchange_flags_off = 0;
+    bool exchange_connected = false;
+    std::vector<void*> peer_opened;             // cudaIpcOpenMemHandle mappings to close
     ~bp_search()
     {
         for (cudaEvent_t e : ev) cudaEventDestroy(e);
@@ -166,6 +145,8 @@ int bp_search_destroy(bp_search* s)
     if (!s) return BP_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    for (void* mapped : s->peer_opened) cudaIpcCloseMemHandle(mapped);
+    if (s->d_exchange) cudaFree(s->d_exchange);
     if (s->arena_from_ctx) s->ctx->arena_busy = false;
     else if (s->arena) cudaFree(s->arena);
     delete s;
@@ -266,29 +247,25 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     }
     p.use_lanes = lanes_ok ? 1 : 0;
 
-    // resident classes: problem lists, ring capacities (every unit that can be outstanding)
-    std::vector<int> rcls_problems;
-    s->h_queues.assign(RS_CLASSES, UnitQueue{});
-    if (p.use_lanes) {
-        std::vector<std::vector<int>> by_rcls(RS_CLASSES);
-        for (int i = 0; i < n_problems; ++i) by_rcls[resident_class_of(s->h_desc[i].cls)].push_back(i);
-        const size_t upc = (size_t)std::min(p.n_chunks, MAX_UNITS_PER_CHILD);
-        for (int c = 0; c < RS_CLASSES; ++c) {
-            s->rcls_count[c] = (int)by_rcls[c].size();
-            s->rcls_prob_off[c] = (int)rcls_problems.size();
-            s->rcls_slot_off[c] = s->n_slots;
-            if (!s->rcls_count[c]) continue;
-            s->rclasses.push_back(c);
-            rcls_problems.insert(rcls_problems.end(), by_rcls[c].begin(), by_rcls[c].end());
-            size_t need = 0;
-            for (int i : by_rcls[c]) need += (size_t)s->h_desc[i].n_entries * upc;
-            size_t cap = 1024;
-            while (cap < need) cap <<= 1;
-            s->n_slots += cap;
-            UnitQueue& q = s->h_queues[c];
-            q.in_flight = s->rcls_count[c];
-            q.cap_mask = (unsigned)(cap - 1);
-        }
+    // resident search: kernel variant by the widest plane / entry mask of the batch; ring sized
+    // for every unit that can be outstanding at once (each live entry of each problem split into
+    // at most gpc_max units), at most 2^20 slots of 8 bytes
+    if (p.use_lanes && n_problems < (1 << RS_PROBLEM_BITS)) {
+        size_t sum_entries = 0;
+        for (int i = 0; i < n_problems; ++i) sum_entries += (size_t)n_entries[i];
+        const bool wide_entries = 2 * max_n > 64;
+        s->variant = (p.ws > 2 ? 2 : 0) + (wide_entries ? 1 : 0);
+        const size_t gpc_cap = (size_t)std::min(p.n_chunks, 256);
+        size_t cap = 1024;
+        while (cap < sum_entries * gpc_cap && cap < (size_t(1) << 20)) cap <<= 1;
+        while (cap < sum_entries) cap <<= 1;
+        s->ring_cap = cap;
+        s->x.cap_mask = (unsigned)(cap - 1);
+        s->x.gpc_max = (int)std::max<size_t>(1, std::min(gpc_cap, cap / std::max<size_t>(sum_entries, 1)));
+        s->x.seed_in_flight = n_problems;
+        double upw = 4.0;
+        if (const char* env = getenv("BP_RESIDENT_UPW")) upw = atof(env);
+        s->x.units_per_warp_x4 = std::max(1, (int)(4.0 * upw + 0.5));
     }
 
     int rc = BP_OK;
@@ -306,13 +283,12 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         p.desc = s->d_desc;
         TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
         TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
-        if (p.use_lanes) {
-            TRY(dev_alloc(s, &s->d_rcls_problems, rcls_problems.size()));
-            TRY(dev_alloc(s, &s->d_queues_init, (size_t)RS_CLASSES));
-        }
         s->up_end = mark();
         if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
-        s->zero_begin = mark();
+        // queue header: its first 256 bytes (head, tail) survive a reset, the rest is zeroed with
+        // the state below and comes back to the host with the result block
+        TRY(dev_alloc(s, &s->x.q, 1));
+        s->zero_begin = s->arena ? reinterpret_cast<char*>(s->x.q) + RS_QUEUE_RESET_OFFSET : nullptr;
         TRY(dev_alloc(s, &p.status, P));
         TRY(dev_alloc(s, &p.depth, P));
         TRY(dev_alloc(s, &p.n_order, P));
@@ -346,8 +322,9 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             TRY(dev_alloc(s, &p.tile, P * p.es));
             TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
             TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
-            TRY(dev_alloc(s, &s->d_queues, (size_t)RS_CLASSES));
-            TRY(dev_alloc(s, &s->d_slots, s->n_slots));
+            TRY(dev_alloc(s, &s->x.ulist, P * p.es));
+            TRY(dev_alloc(s, &s->x.ugeom, P));
+            TRY(dev_alloc(s, &s->x.slots, s->ring_cap));
         }
         TRY(dev_alloc(s, &p.rec, P * p.es * (size_t)p.n_chunks));
         return BP_OK;
@@ -395,10 +372,6 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     put(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc));
     put(s->d_cls_problems, cls_problems.data(), cls_problems.size() * sizeof(int));
     put(s->d_init_tiles, tiles, P * p.es * 2);
-    if (p.use_lanes) {
-        put(s->d_rcls_problems, rcls_problems.data(), rcls_problems.size() * sizeof(int));
-        put(s->d_queues_init, s->h_queues.data(), RS_CLASSES * sizeof(UnitQueue));
-    }
     BP_CUDA(cudaMemcpyAsync(s->up_begin, s->h_upload.data(), s->h_upload.size(), cudaMemcpyHostToDevice,
                             ctx->stream));
     if (boards)
@@ -432,30 +405,21 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             s->grid_lanes[c] = ctx->sm_count * ctx->occ_lanes[c];
         }
     }
-    for (int c : s->rclasses) {
-        if (!ctx->occ_resident[c]) {
+    if (s->ring_cap) {
+        if (!ctx->occ_resident[s->variant]) {
             int per_sm = 1;
-            dispatch_resident(c, [&](auto NBc, auto R, auto Wc, auto E) {
-                cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-                    &per_sm,
-                    fs_search_resident_kernel<decltype(NBc)::value, decltype(R)::value, decltype(Wc)::value,
-                                              decltype(E)::value>,
-                    128, 0);
+            dispatch_resident(s->variant, [&](auto MW, auto ME) {
+                per_sm = ResidentVariant<decltype(MW)::value, decltype(ME)::value>::blocks_per_sm();
             });
-            ctx->occ_resident[c] = std::max(per_sm, 1);
+            ctx->occ_resident[s->variant] = std::max(per_sm, 1);
         }
-        s->grid_resident[c] = ctx->sm_count * ctx->occ_resident[c];
+        s->grid_resident = ctx->sm_count * ctx->occ_resident[s->variant];
+        if (const char* env = getenv("BP_RESIDENT_BLOCKS_PER_SM"))
+            s->grid_resident = ctx->sm_count * std::max(1, std::min(atoi(env), ctx->occ_resident[s->variant]));
     }
     // side streams and fork / join events come from the context's pool
     if (!ctx->fork_event) BP_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     s->fork_ev = ctx->fork_event;
-    for (size_t k = 0; k < s->rclasses.size(); ++k) {
-        cudaStream_t st = side_stream(ctx, k);
-        cudaEvent_t e = side_event(ctx, k);
-        if (!st || !e) { set_error("cannot create a side stream / event"); bp_search_destroy(s); return BP_ERR_CUDA; }
-        s->rcls_stream.push_back(st);
-        s->rcls_done.push_back(e);
-    }
     for (size_t k = 0; k < s->classes.size(); ++k) {
         cudaStream_t st = side_stream(ctx, k);
         cudaEvent_t e = side_event(ctx, k);
@@ -487,6 +451,7 @@ int bp_search_set_partition(bp_search* s, int rank, int n_ranks, int sim_begin, 
 {
     BP_REQUIRE(s != nullptr, "search is null");
     BP_REQUIRE(n_ranks >= 1 && rank >= 0 && rank < n_ranks, "rank / n_ranks");
+    BP_REQUIRE(!s->d_exchange, "the partition is fixed once the exchange buffer exists");
     BP_REQUIRE(sim_begin >= 0 && n_local >= 0 && sim_begin + n_local <= s->p.n_sim, "sim range");
     BP_CUDA(cudaSetDevice(s->ctx->device));
     BP_CUDA(cudaStreamSynchronize(s->ctx->stream));
@@ -497,6 +462,76 @@ int bp_search_set_partition(bp_search* s, int rank, int n_ranks, int sim_begin, 
     s->p.n_chunks = std::max(1, (n_local + CHUNK - 1) / CHUNK);
     s->ready = false;
     return BP_OK;    // the record buffer was sized for all n_sim rollouts
+}
+
+}  // extern "C"
+
+extern "C" {
+
+// Exchange buffer of a partitioned (root-parallel) resident search: the per-child statistics of
+// every rank for the depth in flight, four generations (run parity x depth parity), and one
+// arrival stamp per (problem, rank).  Peers store into it over NVLink from inside their kernels.
+int bp_search_exchange_create(bp_search* s, void* ipc_handle_64, void** local_ptr)
+{
+    BP_REQUIRE(s != nullptr, "search is null");
+    BP_REQUIRE(s->p.n_ranks > 1 && s->p.n_ranks <= RS_MAX_RANKS, "needs a partition over 2..8 ranks");
+    BP_REQUIRE(s->ring_cap != 0, "the resident kernel is not available for this search");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    if (!s->d_exchange) {
+        const size_t stats = (size_t)4 * s->p.n_ranks * s->p.n_problems * s->p.es * sizeof(ChildStats);
+        s->exchange_flags_off = (stats + 255) & ~size_t(255);
+        s->exchange_bytes = s->exchange_flags_off + (size_t)s->p.n_problems * RS_MAX_RANKS * sizeof(int);
+        BP_CUDA(cudaMalloc(&s->d_exchange, s->exchange_bytes));
+        BP_CUDA(cudaMemset(s->d_exchange, 0, s->exchange_bytes));
+    }
+    if (ipc_handle_64) {
+        static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+        cudaIpcMemHandle_t h;
+        BP_CUDA(cudaIpcGetMemHandle(&h, s->d_exchange));
+        memcpy(ipc_handle_64, &h, sizeof(h));
+    }
+    if (local_ptr) *local_ptr = s->d_exchange;
+    return BP_OK;
+}
+
+// ipc_handles: uint8[n_ranks][64] gathered from all ranks (other processes, one per GPU), or
+// local_ptrs: the exchange buffers of n_ranks searches of THIS process (several ranks emulated on
+// one device, or several devices of one process with peer access enabled).
+int bp_search_exchange_connect(bp_search* s, const void* ipc_handles, void* const* local_ptrs)
+{
+    BP_REQUIRE(s != nullptr && s->d_exchange != nullptr, "call bp_search_exchange_create first");
+    BP_REQUIRE((ipc_handles != nullptr) != (local_ptrs != nullptr), "give IPC handles or local pointers");
+    BP_CUDA(cudaSetDevice(s->ctx->device));
+    for (int r = 0; r < s->p.n_ranks; ++r) {
+        char* base = nullptr;
+        if (r == s->p.rank) {
+            base = static_cast<char*>(s->d_exchange);
+        } else if (local_ptrs) {
+            base = static_cast<char*>(local_ptrs[r]);
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, static_cast<const char*>(ipc_handles) + (size_t)r * 64, sizeof(h));
+            void* mapped = nullptr;
+            BP_CUDA(cudaIpcOpenMemHandle(&mapped, h, cudaIpcMemLazyEnablePeerAccess));
+            s->peer_opened.push_back(mapped);
+            base = static_cast<char*>(mapped);
+        }
+        BP_REQUIRE(base != nullptr, "null peer buffer");
+        s->x.gathered[r] = reinterpret_cast<ChildStats*>(base);
+        s->x.arrived[r] = reinterpret_cast<int*>(base + s->exchange_flags_off);
+    }
+    s->exchange_connected = true;
+    return BP_OK;
+}
+
+// blocks per SM of the resident kernel (0 = as many as fit); several searches that must be
+// resident on one device at the same time (ranks emulated on one GPU) share the SMs this way
+int bp_search_set_resident_blocks(bp_search* s, int blocks_per_sm)
+{
+    BP_REQUIRE(s != nullptr && s->ring_cap != 0, "the resident kernel is not available for this search");
+    const int fit = s->ctx->occ_resident[s->variant];
+    s->grid_resident = s->ctx->sm_count * (blocks_per_sm <= 0 ? fit : std::min(blocks_per_sm, fit));
+    return BP_OK;
 }
 
 }  // extern "C"
@@ -563,7 +598,14 @@ int bp_search_reset(bp_search* s)
     if (s->d_init_occ)
         BP_CUDA(cudaMemcpyAsync(p.occ, s->d_init_occ, P * p.rs * p.ws * 4, cudaMemcpyDeviceToDevice, st));
     BP_CUDA(cudaMemcpyAsync(p.tiles, s->d_init_tiles, P * p.es * 2, cudaMemcpyDeviceToDevice, st));
-    s->queues_ready = false;
+    if (s->ring_cap && s->queue_dirty) {
+        // first use (or after an aborted run): empty ring, tickets from zero
+        BP_CUDA(cudaMemsetAsync(s->x.q, 0, RS_QUEUE_RESET_OFFSET, st));
+        BP_CUDA(cudaMemsetAsync(s->x.slots, 0, s->ring_cap * sizeof(unsigned long long), st));
+        s->queue_dirty = false;
+    }
+    s->seeded = false;
+    s->x.run_epoch += 1;
     launch_advance<true>(s, 0, nullptr);
     BP_CUDA(cudaGetLastError());
     s->ran_resident = false;
@@ -579,7 +621,7 @@ int bp_search_set_profiling(bp_search* s, int on)
     BP_CUDA(cudaSetDevice(s->ctx->device));
     s->profiling = on != 0;
     if (s->profiling && s->ev.empty()) {
-        s->ev.resize((size_t)3 * std::max(s->max_depth + 1, RS_CLASSES));
+        s->ev.resize((size_t)3 * (s->max_depth + 1));
         for (cudaEvent_t& e : s->ev) BP_CUDA(cudaEventCreate(&e));
     }
     return BP_OK;
@@ -691,26 +733,26 @@ int bp_search_last_run(bp_search* s, int* resident)
     return BP_OK;
 }
 
-int bp_search_resident_stats(bp_search* s, double* out8)
+int bp_search_resident_stats(bp_search* s, double* out10)
 {
+    double* out8 = out10;
     BP_REQUIRE(s && out8, "null argument");
     BP_CUDA(cudaSetDevice(s->ctx->device));
     BP_CUDA(cudaStreamSynchronize(s->ctx->stream));
-    for (int i = 0; i < 8; ++i) out8[i] = 0.0;
+    for (int i = 0; i < 10; ++i) out8[i] = 0.0;
     if (!s->ran_resident) return BP_OK;
-    std::vector<UnitQueue> queues(RS_CLASSES);
-    BP_CUDA(cudaMemcpy(queues.data(), s->d_queues, RS_CLASSES * sizeof(UnitQueue), cudaMemcpyDeviceToHost));
-    for (int c : s->rclasses) {
-        const UnitQueue& q = queues[c];
-        out8[0] += (double)q.cyc_total;
-        out8[1] += (double)q.cyc_wait;
-        out8[2] += (double)q.cyc_play;
-        out8[3] += (double)q.cyc_advance;
-        out8[4] += (double)q.n_units_played;
-        out8[5] += (double)q.n_advances;
-        out8[6] += (double)q.head;
-        out8[7] += (double)q.tail;
-    }
+    UnitQueue q;
+    BP_CUDA(cudaMemcpy(&q, s->x.q, sizeof(UnitQueue), cudaMemcpyDeviceToHost));
+    out8[0] = (double)q.cyc_total;
+    out8[1] = (double)q.cyc_wait;
+    out8[2] = (double)q.cyc_play;
+    out8[3] = (double)q.cyc_advance;
+    out8[4] = (double)q.n_units_played;
+    out8[5] = (double)q.n_advances;
+    out8[6] = (double)q.n_polls;
+    out8[7] = (double)q.cyc_exchange;
+    out8[8] = (double)q.n_units_published;
+    out8[9] = (double)s->grid_resident * 4.0;
     return BP_OK;
 }
 
@@ -721,71 +763,62 @@ int bp_search_max_depth(bp_search* s, int* max_depth)
     return BP_OK;
 }
 
+// AUTO: the form measured faster on B200
+static int default_mode(const bp_search* s)
+{
+    return BP_SEARCH_STEPPED;
+}
+
 int bp_search_run(bp_search* s)
 {
     BP_REQUIRE(s != nullptr, "search is null");
-    if (s->p.n_ranks != 1) {
-        set_error("bp_search_run is single-rank; use the step API with a partition");
-        return BP_ERR_STATE;
-    }
-    // AUTO = the faster form on this hardware, measured: launch-per-depth
     int mode = s->mode;
     if (const char* env = getenv("BP_SEARCH")) {
         if (strcmp(env, "resident") == 0) mode = BP_SEARCH_RESIDENT;
         else if (strcmp(env, "stepped") == 0) mode = BP_SEARCH_STEPPED;
     }
-    if (mode == BP_SEARCH_RESIDENT && !s->p.use_lanes) {
+    if (mode == BP_SEARCH_AUTO) mode = default_mode(s);
+    if (s->p.n_ranks != 1 && mode != BP_SEARCH_RESIDENT) {
+        set_error("bp_search_run of a partitioned search needs the resident kernel (or use the "
+                  "step API with an all-gather per move)");
+        return BP_ERR_STATE;
+    }
+    if (mode == BP_SEARCH_RESIDENT && !s->ring_cap) {
         set_error("the resident search kernel needs the lane kernel (empty initial boards, equal "
-                  "tiles adjacent in every list; BP_ROLLOUT != warp)");
+                  "tiles adjacent in every list; BP_ROLLOUT != warp) and fewer than 2^20 problems");
         return BP_ERR_STATE;
     }
     if (mode == BP_SEARCH_RESIDENT) {
-        // resident search: one launch per resident class, each on its own stream (the block
-        // scheduler hands the SM slots of warps that leave one class's kernel to the next);
-        // when profiling, serially on the caller's stream with an event pair around each
+        // resident search: seed the queue with depth 0, then one launch plays every depth of
+        // every problem (all shape classes in the same launch)
         if (!s->ready || s->cur_depth != 0) {
             set_error("bp_search_run: call bp_search_reset first");
             return BP_ERR_STATE;
         }
+        if (s->p.n_ranks > 1 && !s->exchange_connected) {
+            set_error("a partitioned resident search needs bp_search_exchange_connect first");
+            return BP_ERR_STATE;
+        }
         BP_CUDA(cudaSetDevice(s->ctx->device));
-        if (!s->queues_ready) {
-            BP_CUDA(cudaMemcpyAsync(s->d_queues, s->d_queues_init, RS_CLASSES * sizeof(UnitQueue),
-                                    cudaMemcpyDeviceToDevice, s->ctx->stream));
-            BP_CUDA(cudaMemsetAsync(s->d_slots, 0, s->n_slots * sizeof(UnitSlot), s->ctx->stream));
-            s->queues_ready = true;
-        }
-        const bool fork = !s->profiling && s->rclasses.size() > 1;
-        if (fork) {
-            BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
-            for (size_t k = 0; k < s->rclasses.size(); ++k)
-                BP_CUDA(cudaStreamWaitEvent(s->rcls_stream[k], s->fork_ev, 0));
-        }
-        for (size_t k = 0; k < s->rclasses.size(); ++k) {
-            const int c = s->rclasses[k];
-            cudaStream_t st = fork ? s->rcls_stream[k] : s->ctx->stream;
-            if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[3 * k], st));
-            dispatch_resident(c, [&](auto NBc, auto R, auto Wc, auto E) {
-                fs_search_resident_kernel<decltype(NBc)::value, decltype(R)::value, decltype(Wc)::value,
-                                          decltype(E)::value>
-                    <<<s->grid_resident[c], 128, 0, st>>>(s->p, s->d_queues + c,
-                                                          s->d_slots + s->rcls_slot_off[c],
-                                                          s->d_rcls_problems + s->rcls_prob_off[c],
-                                                          s->rcls_count[c]);
-            });
+        cudaStream_t st = s->ctx->stream;
+        const unsigned n_warps = (unsigned)s->grid_resident * 4u;
+        if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[0], st));
+        if (!s->seeded) {
+            const int grid = (s->p.n_problems + ADV_WARPS - 1) / ADV_WARPS;
+            fs_resident_seed_kernel<4><<<grid, ADV_WARPS * 32, 0, st>>>(s->p, s->x, n_warps);
             s->ctx->launches++;
-            if (s->profiling) {
-                BP_CUDA(cudaEventRecord(s->ev[3 * k + 1], st));
-                BP_CUDA(cudaEventRecord(s->ev[3 * k + 2], st));
-            }
+            s->seeded = true;
         }
+        dispatch_resident(s->variant, [&](auto MW, auto ME) {
+            ResidentVariant<decltype(MW)::value, decltype(ME)::value>::launch(s->grid_resident, st, s->p, s->x);
+        });
+        s->ctx->launches++;
         BP_CUDA(cudaGetLastError());
-        if (fork) {
-            for (size_t k = 0; k < s->rclasses.size(); ++k) {
-                BP_CUDA(cudaEventRecord(s->rcls_done[k], s->rcls_stream[k]));
-                BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->rcls_done[k], 0));
-            }
+        if (s->profiling) {
+            BP_CUDA(cudaEventRecord(s->ev[1], st));
+            BP_CUDA(cudaEventRecord(s->ev[2], st));
+            s->ev_depths = 1;
         }
-        if (s->profiling) s->ev_depths = (int)s->rclasses.size();
         s->ran_resident = true;
         s->cur_depth = s->max_depth;
         return BP_OK;
@@ -856,31 +889,25 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
     if (child_scores)
         BP_CUDA(cudaMemcpyAsync(child_scores, p.child_scores, P * (p.es / 2) * p.es * 4,
                                 cudaMemcpyDeviceToHost, st));
-    std::vector<UnitQueue> queues;
-    if (s->ran_resident) {
-        queues.resize(RS_CLASSES);
-        BP_CUDA(cudaMemcpyAsync(queues.data(), s->d_queues, RS_CLASSES * sizeof(UnitQueue),
-                                cudaMemcpyDeviceToHost, st));
-    }
     BP_CUDA(cudaStreamSynchronize(st));
-    for (int c : s->rclasses) {
-        if (!s->ran_resident) break;
-        if (queues[c].abort || queues[c].in_flight != 0) {
-            std::vector<int> pending(P);
-            cudaMemcpy(pending.data(), p.pending, P * 4, cudaMemcpyDeviceToHost);
+    if (s->ran_resident) {
+        // the resettable part of the queue header came back with the result block
+        memcpy(reinterpret_cast<char*>(&s->h_queue) + RS_QUEUE_RESET_OFFSET, s->h_results.data(),
+               sizeof(UnitQueue) - RS_QUEUE_RESET_OFFSET);
+        const UnitQueue& q = s->h_queue;
+        if (q.abort || q.in_flight != 0) {
             int stuck = -1, n_stuck = 0;
             for (size_t i = 0; i < P; ++i)
-                if (status[i] == ST_ACTIVE && resident_class_of(s->h_desc[i].cls) == c) {
+                if (status[i] == ST_ACTIVE) {
                     if (stuck < 0) stuck = (int)i;
                     n_stuck++;
                 }
-            set_error("resident search kernel of class %d gave up (abort=%d, %d problems in flight): %s; "
-                      "head=%llu tail=%llu est_units=%d init_done=%u; %d active, first: problem %d "
-                      "depth %d pending %d",
-                      c, queues[c].abort, queues[c].in_flight,
-                      queues[c].abort == 2 ? "unit ring overrun" : "a warp waited too long for work",
-                      queues[c].head, queues[c].tail, queues[c].est_units, queues[c].init_done,
-                      n_stuck, stuck, stuck >= 0 ? depth[stuck] : -1, stuck >= 0 ? pending[stuck] : -1);
+            s->queue_dirty = true;
+            set_error("resident search kernel gave up (abort=%d, %d problems in flight): %s; %d active, "
+                      "first: problem %d depth %d",
+                      q.abort, q.in_flight,
+                      q.abort == 2 ? "unit limit exceeded" : "a warp waited too long for work or for a peer",
+                      n_stuck, stuck, stuck >= 0 ? depth[stuck] : -1);
             return BP_ERR_STATE;
         }
     }

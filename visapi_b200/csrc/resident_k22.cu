@@ -1,0 +1,4 @@
+// resident search kernel, variant <MAXW = 2, MAXEW = 2> (see resident_variant.cuh)
+#define BP_RESIDENT_MAXW 2
+#define BP_RESIDENT_MAXEW 2
+#include "resident_variant.cuh"

@@ -371,6 +371,8 @@ __device__ __forceinline__ ChildStats stats_from_records(const SearchParams& p, 
 }
 
 // merge the per-rank statistics (ranks hold ascending contiguous sim ranges)
+// CG: the buffer was filled by peer-memory stores during this launch (resident search)
+template <bool CG>
 __device__ __forceinline__ ChildStats stats_from_gathered(const SearchParams& p,
                                                           const ChildStats* gathered, int prob,
                                                           int entry)
@@ -381,7 +383,17 @@ __device__ __forceinline__ ChildStats stats_from_gathered(const SearchParams& p,
     st.sum_steps = 0;
     st.prefix_steps = 0;
     for (int g = 0; g < p.n_ranks; ++g) {
-        const ChildStats r = gathered[((size_t)g * p.n_problems + prob) * p.es + entry];
+        const ChildStats* src = gathered + ((size_t)g * p.n_problems + prob) * p.es + entry;
+        ChildStats r;
+        if (CG) {
+            const int2 a = __ldcg(reinterpret_cast<const int2*>(src));
+            r.max_steps = a.x;
+            r.first_solved = (uint32_t)a.y;
+            r.sum_steps = __ldcg(&src->sum_steps);
+            r.prefix_steps = __ldcg(&src->prefix_steps);
+        } else {
+            r = *src;
+        }
         st.max_steps = max(st.max_steps, r.max_steps);
         st.sum_steps += r.sum_steps;
         if (st.first_solved == NONE_U32) {
@@ -445,7 +457,7 @@ template <int RHO, int W, int EJ, bool FIRST, bool RESIDENT>
 __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, int cls,
                                                int cls_list_offset, int next_slot,
                                                const ChildStats* __restrict__ gathered,
-                                               uint16_t* cbuf, UnitQueue* q, UnitSlot* slots,
+                                               uint16_t* cbuf, const ResidentParams* x,
                                                unsigned n_warps)
 {
     constexpr bool CG = RESIDENT;
@@ -482,7 +494,7 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
             st[j].max_steps = 0; st[j].first_solved = NONE_U32;
             st[j].sum_steps = 0; st[j].prefix_steps = 0;
             if (is_child)
-                st[j] = gathered ? stats_from_gathered(p, gathered, prob, e)
+                st[j] = gathered ? stats_from_gathered<CG>(p, gathered, prob, e)
                                  : stats_from_records<CG>(p, prob, e);
             solved_m[j] = __ballot_sync(FULLMASK, is_child && st[j].first_solved != NONE_U32);
             if (first_child < 0 && solved_m[j]) first_child = 32 * j + __ffs(solved_m[j]) - 1;
@@ -624,7 +636,10 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
             }
         }
         if (p.use_lanes) write_lane_tables<CG>(p, prob, d, s, n_alive, placed_r, placed_c, placed_h, placed_w);
-        if (RESIDENT) publish_units<EJ>(p, q, slots, prob, legal, k, cbuf, n_warps);
+        if (RESIDENT) {
+            const int in_flight = __shfl_sync(FULLMASK, ld_volatile(&x->q->in_flight), 0);
+            publish_units<EJ>(p, *x, prob, legal, k, in_flight, n_warps);
+        }
     }
     return status;
 }
@@ -640,7 +655,7 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
     const int idx = blockIdx.x * ADV_WARPS + warp;
     if (idx >= n_cls_problems) return;
     advance_problem<RHO, W, EJ, FIRST, false>(p, cls_problems[idx], cls, cls_list_offset, next_slot,
-                                              gathered, cbuf[warp], nullptr, nullptr, 0u);
+                                              gathered, cbuf[warp], nullptr, 0u);
 }
 
 }  // namespace bp

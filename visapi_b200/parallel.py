@@ -5,9 +5,15 @@
 * root-parallel — one (or a few) hard instances: every rank plays a contiguous slice
   of the N rollouts of EVERY child; once per committed move the per-child statistics
   (max depth, depth sum, first solved rollout, placements before it: 24 bytes per
-  child) are all-gathered over NCCL/NVLink and every rank takes the same first-max
-  decision.  Because each rollout owns a counter-based Philox stream, the result is
-  bit-identical to the single-GPU search for any number of ranks.
+  child) of all ranks are merged and every rank takes the same first-max decision.
+  Because each rollout owns a counter-based Philox stream, the result is bit-identical
+  to the single-GPU search for any number of ranks.  Two forms of the exchange:
+  ``root_parallel_search`` (default, "resident"): ONE kernel launch per rank plays the whole
+  search; the warp that finishes a problem's depth stores its rank's statistics into every
+  rank's buffer over NVLink peer memory (CUDA IPC mappings), raises a flag and waits for
+  the others' flags inside the kernel — no host step, no NCCL call per move.
+  ``root_parallel_search(..., exchange="nccl")``: launch-per-depth kernels with one
+  ``all_gather_into_tensor`` per move (the round-1 form, kept as the cross-check).
 """
 import numpy as np
 
@@ -54,8 +60,52 @@ class _DevicePointer(object):
                                          "data": (int(ptr), False), "version": 2}
 
 
+class ResidentRootParallel(object):
+    """A root-parallel search kept across runs: partition, peer-memory exchange buffers (CUDA IPC
+    handles swapped once over torch.distributed), then ``run()`` = reset + ONE resident kernel
+    launch per rank.  Every rank must construct, run and close it together."""
+
+    def __init__(self, engine, batch, n_sim, strategy, seed, streams=None, group=None):
+        import torch
+        import torch.distributed as dist
+
+        self.group = group
+        self.dist = dist if dist.is_initialized() else None
+        world = dist.get_world_size(group) if self.dist else 1
+        rank = dist.get_rank(group) if self.dist else 0
+        self.world, self.rank = world, rank
+        self.search = engine.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"],
+                                    n_sim, strategy, seed, streams)
+        self.search.set_mode("resident")
+        if world > 1:
+            begin, n_local = split_sims(n_sim, rank, world)
+            self.search.set_partition(rank, world, begin, n_local)
+            handle, _ = self.search.exchange_create()
+            mine = torch.from_numpy(handle).cuda()
+            every = torch.empty(world * 64, dtype=torch.uint8, device=mine.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            self.search.exchange_connect(ipc_handles=every.cpu().numpy().reshape(world, 64))
+            dist.barrier(group=group)
+
+    def run(self):
+        self.search.reset()
+        self.search.run()
+
+    def results(self, want_scores=False):
+        return self.search.results(want_scores=want_scores)
+
+    def close(self):
+        if self.search is not None:
+            if self.dist and self.world > 1:
+                import torch
+                torch.cuda.synchronize()
+                self.dist.barrier(group=self.group)      # nobody stores into a freed buffer
+            self.search.close()
+            self.search = None
+
+
 def root_parallel_search(engine, batch, n_sim, strategy, seed, streams=None, group=None,
-                         want_scores=False, profile=None):
+                         want_scores=False, profile=None, exchange="resident"):
     """Flat search of ``batch`` (datasets.batch_arrays) with the rollouts of every child split
     over the ranks of ``group``.  Must be called by every rank, on the CUDA stream the engine
     was given (torch's current stream).  Returns the same dict as Engine.flat_search."""
@@ -64,6 +114,13 @@ def root_parallel_search(engine, batch, n_sim, strategy, seed, streams=None, gro
 
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if exchange == "resident":
+        rp = ResidentRootParallel(engine, batch, n_sim, strategy, seed, streams, group)
+        try:
+            rp.run()
+            return rp.results(want_scores=want_scores)
+        finally:
+            rp.close()
     search = engine.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim,
                            strategy, seed, streams)
     try:
