@@ -207,11 +207,12 @@ int bp_search_max_depth(bp_search *s, int *max_depth);
 int bp_search_info(bp_search *s, int *lane_kernel, int *n_classes);
 /* resident = 1 when the last bp_search_run used the resident kernel */
 int bp_search_last_run(bp_search *s, int *resident);
-/* Where the warps of the last resident run spent their time; synchronises.  out10 = SM clock
+/* Where the warps of the last resident run spent their time; synchronises.  out13 = SM clock
  * cycles summed over all warps: {resident, waiting for a unit, playing units, advancing
  * problems}, then {units played, problems advanced, polls of an empty slot}, cycles spent in
- * the peer-memory exchange (root-parallel), units published, warps launched. */
-int bp_search_resident_stats(bp_search *s, double *out10);
+ * the peer-memory exchange (root-parallel), units published, warps launched, and the cycles of
+ * the advance by phase {merging the unit records, commit + expand, publishing the next depth}. */
+int bp_search_resident_stats(bp_search *s, double *out13);
 /* synchronises the stream and copies results to the host
  *   results      : bp_search_result[n_problems]
  *   order        : NULL or uint8[n_problems][entry_stride / 2 + 2][2]  solution_tiles_order

@@ -49,6 +49,7 @@ def child(a):
                                                + res["depth"].astype(np.uint64)))}
     if s.last_run_resident():
         out["resident"] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.resident_stats().items()}
+        out["resident"]["advance_cycles"] = {k: int(v) for k, v in out["resident"]["advance_cycles"].items()}
     if a.dump:
         np.save(a.dump, np.stack([res["placements_executed"], res["rollouts_executed"],
                                   res["depth"], res["solution_found"]]))

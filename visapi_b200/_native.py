@@ -10,7 +10,7 @@ import threading
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "librectpack_b200.so")
+LIB_PATH = os.environ.get("BP_LIB") or os.path.join(_HERE, "librectpack_b200.so")
 
 MAX_ROWS = MAX_COLS = MAX_ENTRIES = 128
 
@@ -397,14 +397,16 @@ class Search(object):
 
     def resident_stats(self):
         """Time split of the warps of the last resident run (see bp_search_resident_stats)."""
-        out = (C.c_double * 10)()
+        out = (C.c_double * 13)()
         self.engine._check(self._lib.bp_search_resident_stats(self._h, out))
         tot = max(out[0], 1.0)
         return {"warp_cycles": out[0], "wait_frac": out[1] / tot, "play_frac": out[2] / tot,
                 "advance_frac": out[3] / tot, "exchange_frac": out[7] / tot,
                 "other_frac": (out[0] - out[1] - out[2] - out[3] - out[7]) / tot,
                 "units_played": int(out[4]), "advances": int(out[5]), "polls": int(out[6]),
-                "units_published": int(out[8]), "warps": int(out[9])}
+                "units_published": int(out[8]), "warps": int(out[9]),
+                "advance_cycles": {"merge": out[10] / max(out[5], 1.0), "commit": out[11] / max(out[5], 1.0),
+                                   "publish": out[12] / max(out[5], 1.0)}}
 
     def set_profiling(self, on=True):
         self.engine._check(self._lib.bp_search_set_profiling(self._h, int(bool(on))))

@@ -66,6 +66,35 @@ static void dispatch_resident(int variant, F&& f)
     }
 }
 
+// every block reports the SM it runs on (one wave of small blocks covers every SM)
+__global__ void probe_smid_kernel(unsigned* seen, int n)
+{
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    if (threadIdx.x == 0 && smid < (unsigned)n) seen[smid] = 1u;
+    // stay a little so that the wave spreads over all SMs instead of recycling the first ones
+    const long long t0 = clock64();
+    while (clock64() - t0 < 20000) {}
+}
+
+static int probe_smids(bp_context* ctx)
+{
+    if (ctx->smid_state) return BP_OK;
+    const int n = ctx->sm_count;
+    unsigned* d_seen = nullptr;
+    BP_CUDA(cudaMalloc(&d_seen, n * sizeof(unsigned)));
+    BP_CUDA(cudaMemsetAsync(d_seen, 0, n * sizeof(unsigned), ctx->stream));
+    probe_smid_kernel<<<n * 8, 128, 0, ctx->stream>>>(d_seen, n);
+    std::vector<unsigned> seen(n);
+    BP_CUDA(cudaMemcpyAsync(seen.data(), d_seen, n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
+    BP_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(d_seen);
+    int ok = 1;
+    for (int i = 0; i < n; ++i) ok = ok && seen[i];
+    ctx->smid_state = ok ? 1 : -1;
+    return BP_OK;
+}
+
 struct bp_search {
     bp_context* ctx = nullptr;
     SearchParams p{};
@@ -114,8 +143,8 @@ struct bp_search {
     size_t ring_cap = 0;
     UnitQueue h_queue{};                        // header as read back by bp_search_results
     // root-parallel exchange over peer memory (resident search with n_ranks > 1)
-    void* d_exchange = nullptr;                 // own buffer: gathered[4][R][P][ES] + arrived[P][8]
-    size_t exchange_bytes = 0, exchange_flags_off = 0;
+    void* d_exchange = nullptr;                 // own buffer: gathered[4][R][P][ES] + arrived[P][8] + peer table
+    size_t exchange_bytes = 0, exchange_flags_off = 0, exchange_table_off = 0;
     bool exchange_connected = false;
     std::vector<void*> peer_opened;             // cudaIpcOpenMemHandle mappings to close
     ~bp_search()
@@ -263,6 +292,12 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         s->x.cap_mask = (unsigned)(cap - 1);
         s->x.gpc_max = (int)std::max<size_t>(1, std::min(gpc_cap, cap / std::max<size_t>(sum_entries, 1)));
         s->x.seed_in_flight = n_problems;
+        size_t done_cap = 64;
+        while (done_cap < (size_t)n_problems) done_cap <<= 1;
+        s->x.done_mask = (unsigned)(done_cap - 1);
+        // SMs that advance problems instead of playing (32 warps each)
+        s->x.n_server_sms = n_problems >= 64 ? 2 : 1;
+        if (const char* env = getenv("BP_RESIDENT_SERVERS")) s->x.n_server_sms = std::max(1, atoi(env));
         double upw = 4.0;
         if (const char* env = getenv("BP_RESIDENT_UPW")) upw = atof(env);
         s->x.units_per_warp_x4 = std::max(1, (int)(4.0 * upw + 0.5));
@@ -322,9 +357,13 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             TRY(dev_alloc(s, &p.tile, P * p.es));
             TRY(dev_alloc(s, &p.wmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
             TRY(dev_alloc(s, &p.hmask, P * LANES_TABLE_ROWS * LANES_MASK_WORDS));
+            TRY(dev_alloc(s, &p.alive, P));
+            s->x.urec_stride = std::min(p.es * s->x.gpc_max, (int)RS_MAX_UNITS);
+            TRY(dev_alloc(s, &s->x.urec, P * (size_t)s->x.urec_stride));
             TRY(dev_alloc(s, &s->x.ulist, P * p.es));
-            TRY(dev_alloc(s, &s->x.ugeom, P));
+            TRY(dev_alloc(s, &p.pstate, P));
             TRY(dev_alloc(s, &s->x.slots, s->ring_cap));
+            TRY(dev_alloc(s, &s->x.done_slots, (size_t)s->x.done_mask + 1));
         }
         TRY(dev_alloc(s, &p.rec, P * p.es * (size_t)p.n_chunks));
         return BP_OK;
@@ -406,6 +445,11 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         }
     }
     if (s->ring_cap) {
+        rc = probe_smids(ctx);
+        if (rc) { bp_search_destroy(s); return rc; }
+        if (ctx->smid_state < 0) s->ring_cap = 0;      // no resident search on this device
+    }
+    if (s->ring_cap) {
         if (!ctx->occ_resident[s->variant]) {
             int per_sm = 1;
             dispatch_resident(s->variant, [&](auto MW, auto ME) {
@@ -480,7 +524,9 @@ int bp_search_exchange_create(bp_search* s, void* ipc_handle_64, void** local_pt
     if (!s->d_exchange) {
         const size_t stats = (size_t)4 * s->p.n_ranks * s->p.n_problems * s->p.es * sizeof(ChildStats);
         s->exchange_flags_off = (stats + 255) & ~size_t(255);
-        s->exchange_bytes = s->exchange_flags_off + (size_t)s->p.n_problems * RS_MAX_RANKS * sizeof(int);
+        s->exchange_table_off =
+            (s->exchange_flags_off + (size_t)s->p.n_problems * RS_MAX_RANKS * sizeof(int) + 255) & ~size_t(255);
+        s->exchange_bytes = s->exchange_table_off + sizeof(ResidentParams::PeerTable);
         BP_CUDA(cudaMalloc(&s->d_exchange, s->exchange_bytes));
         BP_CUDA(cudaMemset(s->d_exchange, 0, s->exchange_bytes));
     }
@@ -502,6 +548,7 @@ int bp_search_exchange_connect(bp_search* s, const void* ipc_handles, void* cons
     BP_REQUIRE(s != nullptr && s->d_exchange != nullptr, "call bp_search_exchange_create first");
     BP_REQUIRE((ipc_handles != nullptr) != (local_ptrs != nullptr), "give IPC handles or local pointers");
     BP_CUDA(cudaSetDevice(s->ctx->device));
+    ResidentParams::PeerTable table{};
     for (int r = 0; r < s->p.n_ranks; ++r) {
         char* base = nullptr;
         if (r == s->p.rank) {
@@ -517,9 +564,12 @@ int bp_search_exchange_connect(bp_search* s, const void* ipc_handles, void* cons
             base = static_cast<char*>(mapped);
         }
         BP_REQUIRE(base != nullptr, "null peer buffer");
-        s->x.gathered[r] = reinterpret_cast<ChildStats*>(base);
-        s->x.arrived[r] = reinterpret_cast<int*>(base + s->exchange_flags_off);
+        table.gathered[r] = reinterpret_cast<ChildStats*>(base);
+        table.arrived[r] = reinterpret_cast<int*>(base + s->exchange_flags_off);
     }
+    char* own = static_cast<char*>(s->d_exchange);
+    BP_CUDA(cudaMemcpy(own + s->exchange_table_off, &table, sizeof(table), cudaMemcpyHostToDevice));
+    s->x.peers = reinterpret_cast<const ResidentParams::PeerTable*>(own + s->exchange_table_off);
     s->exchange_connected = true;
     return BP_OK;
 }
@@ -602,6 +652,7 @@ int bp_search_reset(bp_search* s)
         // first use (or after an aborted run): empty ring, tickets from zero
         BP_CUDA(cudaMemsetAsync(s->x.q, 0, RS_QUEUE_RESET_OFFSET, st));
         BP_CUDA(cudaMemsetAsync(s->x.slots, 0, s->ring_cap * sizeof(unsigned long long), st));
+        BP_CUDA(cudaMemsetAsync(s->x.done_slots, 0, ((size_t)s->x.done_mask + 1) * sizeof(unsigned long long), st));
         s->queue_dirty = false;
     }
     s->seeded = false;
@@ -733,13 +784,13 @@ int bp_search_last_run(bp_search* s, int* resident)
     return BP_OK;
 }
 
-int bp_search_resident_stats(bp_search* s, double* out10)
+int bp_search_resident_stats(bp_search* s, double* out13)
 {
-    double* out8 = out10;
+    double* out8 = out13;
     BP_REQUIRE(s && out8, "null argument");
     BP_CUDA(cudaSetDevice(s->ctx->device));
     BP_CUDA(cudaStreamSynchronize(s->ctx->stream));
-    for (int i = 0; i < 10; ++i) out8[i] = 0.0;
+    for (int i = 0; i < 13; ++i) out8[i] = 0.0;
     if (!s->ran_resident) return BP_OK;
     UnitQueue q;
     BP_CUDA(cudaMemcpy(&q, s->x.q, sizeof(UnitQueue), cudaMemcpyDeviceToHost));
@@ -753,6 +804,9 @@ int bp_search_resident_stats(bp_search* s, double* out10)
     out8[7] = (double)q.cyc_exchange;
     out8[8] = (double)q.n_units_published;
     out8[9] = (double)s->grid_resident * 4.0;
+    out8[10] = (double)q.cyc_adv_merge;
+    out8[11] = (double)q.cyc_adv_commit;
+    out8[12] = (double)q.cyc_adv_publish;
     return BP_OK;
 }
 
@@ -801,11 +855,17 @@ int bp_search_run(bp_search* s)
         }
         BP_CUDA(cudaSetDevice(s->ctx->device));
         cudaStream_t st = s->ctx->stream;
-        const unsigned n_warps = (unsigned)s->grid_resident * 4u;
+        const int blocks_per_sm = s->grid_resident / s->ctx->sm_count;
+        if (s->x.n_server_sms >= s->ctx->sm_count) {
+            set_error("resident search: %d server SMs leave nothing to play on", s->x.n_server_sms);
+            return BP_ERR_STATE;
+        }
+        s->x.n_roll_warps = (s->ctx->sm_count - s->x.n_server_sms) * blocks_per_sm * 4;
+        const unsigned n_warps = (unsigned)s->x.n_roll_warps;
         if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[0], st));
         if (!s->seeded) {
             const int grid = (s->p.n_problems + ADV_WARPS - 1) / ADV_WARPS;
-            fs_resident_seed_kernel<4><<<grid, ADV_WARPS * 32, 0, st>>>(s->p, s->x, n_warps);
+            fs_resident_seed_kernel<0><<<grid, ADV_WARPS * 32, 0, st>>>(s->p, s->x, n_warps);
             s->ctx->launches++;
             s->seeded = true;
         }

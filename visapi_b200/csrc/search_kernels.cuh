@@ -1,6 +1,6 @@
 // Flat search kernels with one launch per depth: the two rollout kernels (warp-per-board,
 // lane-per-rollout), the per-problem advance (score children, commit, expand, lane tables) and
-// the root-parallel reduce.  advance_problem is also what the resident kernel calls.
+// the root-parallel reduce.
 #pragma once
 #include "search_queue.cuh"
 #include "search_types.cuh"
@@ -450,17 +450,16 @@ __device__ __forceinline__ void compact_entries_adv(WarpState<RHO, W, EJ>& s, ui
 // One warp, one problem.  FIRST: set up depth 0.  Otherwise: score the children of the
 // current depth (lane = child), stop at the first child with a solved rollout, else commit
 // the first maximum; then expand the new state (LFB, legal entries, lane tables) and hand the
-// children of the next depth to the rollout kernels: appended to the class's child list
-// (one launch per depth) or, RESIDENT, published as units on the queue.
-// Returns the problem's status.
-template <int RHO, int W, int EJ, bool FIRST, bool RESIDENT>
+// children of the next depth to the rollout kernels (appended to the class's child list).
+// (The resident kernel advances problems in the skyline state instead: advance_skyline,
+// search_resident.cuh.)  Returns the problem's status.
+template <int RHO, int W, int EJ, bool FIRST>
 __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, int cls,
                                                int cls_list_offset, int next_slot,
                                                const ChildStats* __restrict__ gathered,
-                                               uint16_t* cbuf, const ResidentParams* x,
-                                               unsigned n_warps)
+                                               uint16_t* cbuf)
 {
-    constexpr bool CG = RESIDENT;
+    constexpr bool CG = false;
     const int lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     const ProblemDesc d = p.desc[prob];
@@ -620,25 +619,23 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
         if (status != ST_SOLVED && n_alive > 0 && r >= 0)
             atomicAdd(p.n_tiles_placed + prob, (unsigned long long)n_alive);   // one attempt per entry (:60)
         if (k > 0) {
-            if (!RESIDENT) base = atomicAdd(&p.child_count[next_slot * FS_CLASSES + cls], (unsigned)k);
+            base = atomicAdd(&p.child_count[next_slot * FS_CLASSES + cls], (unsigned)k);
             atomicAdd(p.rollouts_executed + prob, (unsigned long long)k * p.n_local);
         }
     }
     if (k > 0) {
-        if (!RESIDENT) {
-            base = __shfl_sync(FULLMASK, base, 0);
+        base = __shfl_sync(FULLMASK, base, 0);
 #pragma unroll
-            for (int j = 0; j < EJ; ++j) {
-                if ((legal[j] >> lane) & 1u)
-                    p.child_list[cls_list_offset + base + __popc(legal[j] & lt)] =
-                        (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
-                base += __popc(legal[j]);
-            }
+        for (int j = 0; j < EJ; ++j) {
+            if ((legal[j] >> lane) & 1u)
+                p.child_list[cls_list_offset + base + __popc(legal[j] & lt)] =
+                    (uint32_t)prob | ((uint32_t)(lane + 32 * j) << 24);
+            base += __popc(legal[j]);
         }
         if (p.use_lanes) write_lane_tables<CG>(p, prob, d, s, n_alive, placed_r, placed_c, placed_h, placed_w);
-        if (RESIDENT) {
-            const int in_flight = __shfl_sync(FULLMASK, ld_volatile(&x->q->in_flight), 0);
-            publish_units<EJ>(p, *x, prob, legal, k, in_flight, n_warps);
+        if (FIRST && p.use_lanes && lane == 0) {               // skyline state of the resident search
+            p.alive[prob] = make_uint4(word_range(0, n_alive, 0), word_range(0, n_alive, 1),
+                                       word_range(0, n_alive, 2), word_range(0, n_alive, 3));
         }
     }
     return status;
@@ -654,8 +651,8 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
     const int warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * ADV_WARPS + warp;
     if (idx >= n_cls_problems) return;
-    advance_problem<RHO, W, EJ, FIRST, false>(p, cls_problems[idx], cls, cls_list_offset, next_slot,
-                                              gathered, cbuf[warp], nullptr, 0u);
+    advance_problem<RHO, W, EJ, FIRST>(p, cls_problems[idx], cls, cls_list_offset, next_slot, gathered,
+                                       cbuf[warp]);
 }
 
 }  // namespace bp

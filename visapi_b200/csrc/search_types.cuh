@@ -42,6 +42,22 @@ struct __align__(8) ChildStats {
     long long prefix_steps;  // placements up to and including first_solved (this rank)
 };
 
+// Everything the resident kernel changes in a problem from depth to depth, in ONE 128-byte
+// record: a playout reads three 16-byte words of it, the advance reads and writes it whole, and
+// the counters need no atomics (only the advancing warp touches them).  The arrays the host
+// reads (status, depth, n_order, counters) are written once, when the problem is finished.
+struct __align__(16) ProbState {
+    int depth, n_alive, hmin, col;                 // word 0: depth; live entries; first free cell
+    int run, k, group, gpc;                        // word 1: free run; legal children; chunks per unit, units per child
+    uint32_t legal[4];                             // word 2: legal entries of the initial tile list
+    uint32_t alive[4];                             // word 3: live entries of the initial tile list
+    int n_order, prev_tile, status, pad0;          // word 4
+    unsigned long long n_tiles_placed, rollouts;                   // word 5
+    unsigned long long rollout_placements, rollouts_executed;      // word 6
+    unsigned long long placements_executed, pad1;                  // word 7
+};
+static_assert(sizeof(ProbState) == 128, "one cache line");
+
 struct SearchParams {
     int n_problems, es, rs, ws;
     int n_sim, strategy, n_chunks;          // n_chunks: chunks of THIS rank
@@ -76,8 +92,11 @@ struct SearchParams {
     uint4* tile;             // [P][ES] (h, w, width mask (1 << w) - 1 as lo / hi word)
     uint32_t* wmask;         // [P][129][4] entries with w <= x
     uint32_t* hmask;         // [P][129][4] entries with h <= y
-    // resident (single-launch) search: units of the current depth of each problem still running
+    // resident (single-launch) search: units of the current depth of each problem still running,
+    // and the live entries of the initial (never compacted) tile list
     int* pending;            // [P]
+    uint4* alive;            // [P] (as the reset leaves it; the resident kernel continues in pstate)
+    ProbState* pstate;       // [P]
 };
 
 // loads of state another warp of the SAME launch may have written: through L2 (ld.global.cg),
