@@ -269,6 +269,10 @@ int bp_tree_check(bp_tree *t, int *overflow);
 int bp_tree_root_counts(bp_tree *t, int32_t *counts, int32_t *n_nodes);
 /* same counts left on the device (int32[n_trees][n_entries]) for an NCCL all-reduce */
 int bp_tree_root_counts_dev(bp_tree *t, void **counts_dev, int64_t *n_bytes);
+/* root-parallel PUCT (independent trees per GPU from the same roots): Nsa (int32) and
+ * Wsa = Qsa * Nsa (float64), both [n_trees][n_entries], left on the device; the ranks all-reduce
+ * SUM both before getActionProb (binpack/MCTS.py:221-244 consumes the counts). */
+int bp_tree_root_stats_dev(bp_tree *t, void **counts_dev, void **wsa_dev);
 int bp_tree_destroy(bp_tree *t);
 
 #ifdef __cplusplus

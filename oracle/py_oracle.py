@@ -389,6 +389,14 @@ class PuctTree(object):
         self.Ns[s] += 1
         return v
 
+    def root_stats(self, state):
+        """Visit counts Nsa and value sums Wsa = Qsa * Nsa of the root's actions: what the ranks
+        of a root-parallel PUCT search sum before :221-244 forms the policy."""
+        s = self.base.with_state(state).key()
+        counts = [self.Nsa.get((s, a), 0) for a in range(self.action_size())]
+        wsa = [self.Qsa.get((s, a), 0.0) * self.Nsa.get((s, a), 0) for a in range(self.action_size())]
+        return counts, wsa
+
     def action_prob(self, state, temp=1):
         """:221-244."""
         for _ in range(self.num_sims):

@@ -90,3 +90,51 @@ def test_root_parallel_merge_world2(golden, tmp_path):
             assert merged[0][k]["prefix_steps"] == sum(r["steps"] for r in steps[:hit[0] + 1])
         else:
             assert merged[0][k]["first_solved"] == parallel.NONE_U32
+
+
+def _puct_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    from oracle import py_oracle
+    from visapi_b200 import parallel
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank searches its OWN tree from the same root (CPU oracle tree, deterministic stub
+    # net); a different number of simulations per rank stands in for different random streams
+    h, w, n = 8, 8, 6
+    tiles = np.array([[2, 2], [4, 2], [2, 4], [4, 4], [2, 8], [8, 2], [2, 2], [2, 4], [4, 2], [4, 4], [8, 2], [2, 8]])
+
+    def predict(grid, _tiles):
+        filled = int(np.count_nonzero(np.asarray(grid)))
+        pi = np.array([float((a * 7 + filled * 3) % 11 + 1) for a in range(2 * n)])
+        return pi / pi.sum(), (filled % 8) / 8.0
+    tree = py_oracle.PuctTree(py_oracle.Board(h, w, tiles.tolist(), n), predict, 0, 1.0)
+    root = (np.zeros((h, w)), tiles.copy())
+    for _ in range(30 + 17 * rank):
+        tree.search(root)
+    counts, wsa = tree.root_stats(root)
+    c = torch.tensor(counts, dtype=torch.int32).view(1, -1)
+    wv = torch.tensor(wsa, dtype=torch.float64).view(1, -1)
+    np.save(os.path.join(out_dir, "own_%d.npy" % rank), np.stack([c.numpy()[0].astype(np.float64), wv.numpy()[0]]))
+    mc, mw, mq = parallel.allreduce_root_stats(c, wv)
+    probs = parallel.probs_from_counts(mc.numpy(), 1)
+    np.save(os.path.join(out_dir, "merged_puct_%d.npy" % rank),
+            np.stack([mc.numpy()[0].astype(np.float64), mw.numpy()[0], mq.numpy()[0], probs[0]]))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_puct_root_parallel_allreduce_world2(tmp_path):
+    """SURVEY 8e row 3 on two gloo ranks: root Nsa / Wsa summed over ranks, policy from the sum."""
+    world = 2
+    mp.spawn(_puct_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    own = [np.load(tmp_path / ("own_%d.npy" % r)) for r in range(world)]
+    merged = [np.load(tmp_path / ("merged_puct_%d.npy" % r)) for r in range(world)]
+    np.testing.assert_array_equal(merged[0], merged[1])                  # every rank holds the same merge
+    np.testing.assert_array_equal(merged[0][0], own[0][0] + own[1][0])   # counts: sum rule
+    np.testing.assert_allclose(merged[0][1], own[0][1] + own[1][1])      # value sums
+    assert not np.array_equal(own[0][0], own[1][0])                      # the ranks' trees differ
+    c = merged[0][0]
+    np.testing.assert_allclose(merged[0][3], c / c.sum())
+    np.testing.assert_allclose(merged[0][2] * c, merged[0][1])

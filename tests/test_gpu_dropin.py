@@ -1,6 +1,8 @@
 """The reference-facing Python surface (SolutionChecker, State, CustomMCTS, BinPackGame,
 MCTS) against the reference's own unit-test vectors and the reference-made fixtures.
 Everything here runs the CUDA path: marked gpu."""
+import os
+
 import numpy as np
 import pytest
 
@@ -379,3 +381,246 @@ def test_device_leaf_path_matches_host_path():
     # a few visits when two UCB values are nearly tied, never by much
     assert np.abs(ch[0] - cd[0]).max() <= 3
     assert (cd[1] > 1).all()
+
+
+def _exact_nets(h, w, n):
+    """Host and device nets whose outputs are exactly representable in float32 (small integers
+    as unnormalised policy, eighths as value): masking and normalising them gives the same
+    float64 priors on both paths, so the two searches must agree visit for visit."""
+    import torch
+
+    def predict_batch(gr):
+        pis, vs = [], []
+        for g in gr:
+            f = int(np.count_nonzero(g))
+            pis.append(np.array([float((a * 7 + f * 3) % 11 + 1) for a in range(2 * n)]))
+            vs.append((f % 8) / 8.0)
+        return np.array(pis), np.array(vs)
+
+    def predict_dev(gr, tl):
+        f = gr.sum(dim=(1, 2)).to(torch.int64)
+        a = torch.arange(2 * n, dtype=torch.int64, device=gr.device)
+        p = ((a[None, :] * 7 + f[:, None] * 3) % 11 + 1).to(torch.float32)
+        return p, ((f % 8).to(torch.float32) / 8.0)
+    return predict_batch, predict_dev
+
+
+def _random_roots(h, w, n, B, seed):
+    from visapi_b200.game import BinPackGame
+    np.random.seed(seed)
+    games = [BinPackGame(h, w, n) for _ in range(B)]
+    tiles = np.array([[[int(t[0]), int(t[1])] for t in g._base_board.tiles] for g in games])
+    return np.zeros((B, h, w)), tiles
+
+
+def test_device_leaf_path_is_exact_with_float32_exact_net():
+    """The device-leaf path (the fast one) against the host-leaf path, visit for visit."""
+    from visapi_b200.puct import BatchedMCTS
+    h, w, n, B, sims = 10, 10, 8, 6, 60
+    grids, tiles = _random_roots(h, w, n, B, 3)
+    predict_batch, predict_dev = _exact_nets(h, w, n)
+    host = BatchedMCTS(h, w, 2 * n, predict_batch, sims, 1.0, B)
+    host.set_roots(grids, tiles)
+    host.simulate()
+    dev = BatchedMCTS(h, w, 2 * n, None, sims, 1.0, B)
+    dev.set_roots(grids, tiles)
+    dev.simulate_on_device(predict_dev)
+    ch, cd = host._tree.root_counts(), dev._tree.root_counts()
+    assert np.array_equal(ch[0], cd[0]) and np.array_equal(ch[1], cd[1])
+    assert np.array_equal(host.action_probs(1), dev.action_probs(1))
+
+
+def test_simulate_on_device_under_a_side_stream():
+    """the engine kernels and the torch ops between them share ONE stream even when
+    the caller runs under torch.cuda.stream(...); same visits as on the default stream."""
+    import torch
+    from visapi_b200.puct import BatchedMCTS
+    h, w, n, B, sims = 10, 10, 8, 16, 40
+    grids, tiles = _random_roots(h, w, n, B, 5)
+    _, predict_dev = _exact_nets(h, w, n)
+    ref = BatchedMCTS(h, w, 2 * n, None, sims, 1.0, B)
+    ref.set_roots(grids, tiles)
+    ref.simulate_on_device(predict_dev)
+    want = ref._tree.root_counts()[0]
+    side = torch.cuda.Stream()
+    for _ in range(3):
+        t = BatchedMCTS(h, w, 2 * n, None, sims, 1.0, B)
+        t.set_roots(grids, tiles)
+        with torch.cuda.stream(side):
+            t.simulate_on_device(predict_dev)
+        side.synchronize()
+        assert np.array_equal(t._tree.root_counts()[0], want)
+    assert ref._tree.engine.stream != side.cuda_stream          # the binding was undone
+
+
+def test_puct_root_parallel_sum_rule():
+    """independent trees per 'rank' from the same roots, root Nsa and Wsa summed
+    before the policy is formed.  Three ranks are emulated by three searches with different
+    numbers of simulations (so their counts differ); with no process group the all-reduce is the
+    identity, so the merge is checked against the sum of the per-rank statistics by hand and
+    against probs_from_counts / getActionProb's rule."""
+    import torch
+    from visapi_b200.parallel import _DevicePointer, allreduce_root_stats, probs_from_counts
+    from visapi_b200.puct import BatchedMCTS
+    h, w, n, B = 10, 10, 8, 5
+    grids, tiles = _random_roots(h, w, n, B, 11)
+    _, predict_dev = _exact_nets(h, w, n)
+    counts_sum = np.zeros((B, 2 * n), np.int64)
+    wsa_sum = np.zeros((B, 2 * n))
+    per_rank = []
+    for sims in (20, 35, 50):
+        t = BatchedMCTS(h, w, 2 * n, None, sims, 1.0, B)
+        t.set_roots(grids, tiles)
+        t.simulate_on_device(predict_dev)
+        probs, q = t.action_probs_root_parallel(temp=1)          # one rank: identity merge
+        assert np.array_equal(probs, t.action_probs(1))
+        c_ptr, w_ptr = t._tree.root_stats_dev()
+        c = torch.as_tensor(_DevicePointer(c_ptr, B * 2 * n * 4), device="cuda").view(torch.int32).view(B, -1)
+        wv = torch.as_tensor(_DevicePointer(w_ptr, B * 2 * n * 8), device="cuda").view(torch.float64).view(B, -1)
+        c, wv = c.cpu().numpy().copy(), wv.cpu().numpy().copy()
+        assert np.array_equal(c, t._tree.root_counts()[0]) and c.sum(axis=1).max() <= sims
+        assert np.allclose(np.where(c > 0, wv / np.maximum(c, 1), 0.0), q)
+        per_rank.append(c)
+        counts_sum += c
+        wsa_sum += wv
+    assert not np.array_equal(per_rank[0] * 3, counts_sum)       # the ranks really differ
+    merged_c, merged_w, merged_q = allreduce_root_stats(torch.from_numpy(counts_sum),
+                                                       torch.from_numpy(wsa_sum))
+    probs = probs_from_counts(merged_c.numpy(), 1)
+    assert np.allclose(probs.sum(axis=1), 1.0)
+    assert np.array_equal(probs, counts_sum / counts_sum.sum(axis=1, keepdims=True))
+    assert np.array_equal(probs_from_counts(counts_sum, 0).argmax(axis=1), counts_sum.argmax(axis=1))
+    assert np.allclose(merged_q.numpy() * counts_sum, wsa_sum)
+
+
+def _game_with_tiles(h, w, n, init_tiles, device=None, np_seed=None):
+    """BinPackGame whose next getInitBoard() hands out ``init_tiles`` (the reference's instance)
+    and then seeds np.random as the fixture generator did at that point."""
+    from visapi_b200.game import BinPackGame, Board
+    np.random.seed(0)
+    game = BinPackGame(h, w, n, device=device)
+    queue = [list(map(list, t)) for t in (init_tiles if isinstance(init_tiles[0][0], list) else [init_tiles])]
+
+    def get_init_board(_g=game, _q=queue):
+        tiles = _q.pop(0)
+        _g._base_board = Board(h, w, [tuple(t) for t in tiles], n, device=_g.device)
+        if np_seed is not None:
+            np.random.seed(np_seed)
+        return _g._base_board.state, _g._base_board.vis_state
+    game.getInitBoard = get_init_board
+    return game
+
+
+def test_coach_episode_matches_reference(golden):
+    """alpha/Coach.py:25-63 run by the reference under the stub net and a seeded np.random
+    (tests/golden/coach_episode.json): the same example stream, bit for bit."""
+    from visapi_b200.coach import Coach
+
+    for case in golden("coach_episode.json"):
+        h, w, n = case["height"], case["width"], case["n_tiles"]
+        stub = _stub_predict(2 * n, [])
+
+        class Net(object):
+            calls = 0
+
+            def predict(self, board):
+                Net.calls += 1
+                return stub.predict(board[0] if isinstance(board, (tuple, list)) else board)
+        args = {"numMCTSSims": case["num_sims"], "cpuct": case["cpuct"], "tempThreshold": case["tempThreshold"]}
+        game = _game_with_tiles(h, w, n, case["init_tiles"], np_seed=case["np_seed"])
+        coach = Coach(game, Net(), args)
+        examples = coach.executeEpisode()
+        assert len(examples) == len(case["examples"])
+        assert Net.calls == case["leaf_evals"]
+        for got, want in zip(examples, case["examples"]):
+            assert hex_rows_of(got[0]) == want["board"]
+            assert [[int(t[0]), int(t[1])] for t in got[1]] == want["tiles"]
+            assert [float(p) for p in got[2]] == want["pi"]
+            assert float(got[3]) == want["reward"]
+
+
+def test_arena_matches_reference(golden):
+    """alpha/Arena.py:26-123 with two scripted players on the reference's instances."""
+    from visapi_b200.arena import Arena
+    for case in golden("arena.json"):
+        h, w, n = case["height"], case["width"], case["n_tiles"]
+        game = _game_with_tiles(h, w, n, case["init_tiles"])
+
+        def first_valid(board, _g=game):
+            return int(np.argmax(_g.getValidMoves(board, 1)))
+
+        def last_valid(board, _g=game):
+            v = np.asarray(_g.getValidMoves(board, 1))
+            return int(len(v) - 1 - np.argmax(v[::-1]))
+        one, two, draws = Arena(first_valid, last_valid, game).playGames(case["games"])
+        assert (one, two, draws) == (case["one_won"], case["two_won"], case["draws"])
+
+
+def _strip(node):
+    counter = [0]
+
+    def walk(n):
+        me = counter[0]
+        counter[0] += 1
+        score = n["score"]
+        return {"name": me, "tiles": [[int(t[0]), int(t[1])] for t in n["tiles"]],
+                "board": hex_rows_of(np.asarray(n["board"])),
+                "tile_placed": None if n["tile_placed"] is None else [int(v) for v in n["tile_placed"]],
+                "score": float(score) if isinstance(score, (float, np.floating, np.integer)) else score,
+                "children": [walk(c) for c in n["children"]]}
+    return walk(node)
+
+
+def test_tree_export_matches_reference(golden):
+    """f3: State.render_to_json() / render_children() of the tree CustomMCTS.predict builds,
+    against the reference's own rendering of its tree (engine/state.py:16-61,88-136,
+    run_mcts.py:227-239) — node for node: tiles, occupancy, tile_placed, score, children."""
+    import re
+    from visapi_b200.mcts import CustomMCTS
+    for case in golden("tree_render.json"):
+        tiles = [tuple(t) for t in case["tiles"]]
+        m = CustomMCTS(tiles, np.zeros((case["rows"], case["cols"])), strategy=case["strategy"],
+                       seed=123, stream=case["stream"])
+        root, depth, found = m.predict(N=case["n_sim"])
+        assert (depth, found) == (case["depth"], case["solution_found"])
+        nested, index = root.render_children(only_ids=False)
+
+        def labels(d):
+            out = []
+            for k, v in d.items():
+                k = re.sub(r"^\(\d+\) ", "", k)
+                k = k.split(" Sim. depth:")[0] + " Sim. depth:" + k.split(" Sim. depth:")[1].split(" ")[0]
+                out.append([k, labels(v)])
+            return out
+        assert labels(nested) == case["labels_before_centralize"]
+        ids, _ = root.render_children(only_ids=True)
+
+        def shape(d):
+            return [shape(v) for v in d.values()]
+        assert shape(ids) == case["ids_shape_before_centralize"]
+        root.centralize_node_with_children()
+        got = _strip(root.render_to_json())
+        want = case["tree"]
+
+        def drop(n):
+            n = dict(n)
+            n.pop("board_max", None)
+            n["score"] = float(n["score"]) if isinstance(n["score"], (int, float)) else n["score"]
+            n["children"] = [drop(c) for c in n["children"]]
+            return n
+        assert drop(got) == drop(want)
+
+
+def test_ascii_tree_dump(tmp_path):
+    """run_mcts.py:268-279: the search tree as the asciitree LeftAligned text next to the JSON."""
+    from visapi_b200.run_mcts import ascii_tree
+    from collections import OrderedDict
+    tree = {"root": OrderedDict([("a", OrderedDict([("a1", {}), ("a2", {})])), ("b", {})])}
+    assert ascii_tree(tree) == "root\n +-- a\n |   +-- a1\n |   +-- a2\n +-- b"
+    from visapi_b200 import run_mcts
+    out = tmp_path / "trees"
+    run_mcts.main(["6", "8", "8", "--n_sim", "5", "--count", "1", "--quiet", "--dump_tree", str(out)])
+    names = sorted(os.listdir(out))
+    assert any(x.endswith("_tree.json") for x in names) and any(x.endswith(".txt") for x in names)
+    text = open(os.path.join(out, [x for x in names if x.endswith(".txt")][0])).read()
+    assert text.startswith("(") and "\n +-- (" in text and "Remaining tiles" in text

@@ -280,3 +280,61 @@ def test_published_aggregates_present(golden):
     assert pub["g"]["max_depth/1000"]["solved"] == 403
     assert pub["g"]["avg_depth/1000"]["solved"] == 461
     assert pub["b"]["avg_depth/5000"]["solved"] == 55
+
+
+def test_as_shipped_reference_versus_occupancy_fix(golden):
+    """parity is pinned to the reference WITH its occupancy bug fixed (cells painted
+    2, 3, ... count as occupied inside predict()).  tests/golden/as_shipped.json holds the truly
+    unmodified reference next to the fixed one on the same instances and Philox streams: the
+    oracle must reproduce the FIXED runs exactly, and the fixture measures the divergence (3 of 24
+    small instances, always the as-shipped code laying a tile over painted cells and "solving")."""
+    from oracle import c_oracle
+    data = golden("as_shipped.json")
+    differ = 0
+    for inst in data["instances"]:
+        tiles = [tuple(t) for t in inst["tiles"]]
+        board = np.zeros((inst["rows"], inst["cols"]))
+        got = c_oracle.flat_search(tiles, board, inst["n_sim"], "max_depth", 123, inst["stream"])
+        for k in ("depth", "solution_found", "n_tiles_placed", "rollouts"):
+            assert got[k] == inst["fixed"][k], (inst["stream"], k)
+        same = all(inst["fixed"][k] == inst["as_shipped"][k] for k in inst["fixed"])
+        assert same == inst["same"]
+        differ += 0 if same else 1
+        if not same:   # the as-shipped run never does worse: overlapping placements only add "fits"
+            assert inst["as_shipped"]["depth"] >= inst["fixed"]["depth"] or inst["as_shipped"]["solution_found"]
+    assert differ == data["n_differ"] and 0 < differ < len(data["instances"]) // 2
+
+
+def test_coach_episode_fixture_against_oracle(golden):
+    """alpha/Coach.py:25-63 as run by the reference (tests/golden/coach_episode.json) against the
+    oracle's PUCT tree and Board: same number of moves, same policies bit for bit, same reward,
+    same number of net evaluations."""
+    from oracle import py_oracle
+
+    def stub(grid, _tiles, size):
+        filled, cells = int(np.count_nonzero(np.asarray(grid))), int(np.asarray(grid).size)
+        pi = np.array([((a * 2654435761 + filled * 40503 + 12345) % 1000 + 1) for a in range(size)],
+                      dtype=np.float64)
+        return pi / pi.sum(), 0.5 * filled / cells
+    for case in golden("coach_episode.json"):
+        h, w, n = case["height"], case["width"], case["n_tiles"]
+        base = py_oracle.Board(h, w, case["init_tiles"], n)
+        tree = py_oracle.PuctTree(base, lambda g, t: stub(g, t, 2 * n), case["num_sims"], case["cpuct"])
+        np.random.seed(case["np_seed"])
+        state = (np.zeros((h, w)), np.array(case["init_tiles"]))
+        step, stream = 0, []
+        while True:
+            step += 1
+            pi = tree.action_prob(state, temp=int(step < case["tempThreshold"]))
+            stream.append((state, pi))
+            action = np.random.choice(len(pi), p=pi)
+            nxt = base.with_state(state).add_tile(action)
+            state = (nxt[0], np.array(nxt[1]))
+            reward = tree.game_ended(base.with_state(state))
+            if reward != 0:
+                break
+        assert len(stream) == len(case["examples"]) and tree.leaf_evals == case["leaf_evals"]
+        for (st, pi), want in zip(stream, case["examples"]):
+            assert [float(p) for p in pi] == want["pi"]
+            assert [[int(t[0]), int(t[1])] for t in st[1]] == want["tiles"]
+            assert float(reward) == want["reward"]

@@ -1,8 +1,10 @@
 #!/usr/bin/env python
 """Config 4: 50 tiles on 25x25 and 40x40 boards from the generator, seeds
 0..7, N = 5000 rollouts per child, root-parallel: every rank plays N/G rollouts of every
-child, per-child statistics all-gathered over NCCL once per committed move.  Run alone or
-under torchrun; prints one JSON line (rank 0) with the time per instance and the proof that
+child; the per-child statistics are merged once per committed move, inside the resident kernels
+over NVLink peer memory (--exchange resident) or by an NCCL all-gather between launches
+(--exchange nccl).  Times reset + search of a search object created once.  Run alone or under
+torchrun; prints one JSON line (rank 0) with the time per instance and the proof that
 the result does not depend on the number of ranks (a digest of all outputs).
 
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
@@ -39,6 +41,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--n-sim", type=int, default=5000)
     ap.add_argument("--seeds", type=int, default=8)
+    ap.add_argument("--exchange", default="resident", choices=["resident", "nccl"])
+    ap.add_argument("--reps", type=int, default=5)
     a = ap.parse_args()
     from visapi_b200 import Engine, datasets, parallel
     from visapi_b200.verify import replay_solution
@@ -50,26 +54,33 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local, stream=torch.cuda.current_stream().cuda_stream)
     n_sim = a.n_sim
-    out = {"world": world, "n_sim": n_sim, "boards": {}}
+    out = {"world": world, "n_sim": n_sim, "exchange": a.exchange, "boards": {}}
     digest = hashlib.sha256()
     for (rows, cols) in ((25, 25), (40, 40)):
         times, depths, found, rollouts = [], [], 0, 0
         for seed in range(a.seeds):
             p = instance(50, rows, cols, seed)
             batch = datasets.batch_arrays([p])
-            for rep in range(2):                                  # second run is timed
+            rp = parallel.RootParallelSearch(eng, batch, n_sim, 0, 123, np.array([seed], np.uint32),
+                                             exchange=a.exchange)
+            best = None
+            for rep in range(a.reps + 1):                          # the first run warms up
                 torch.cuda.synchronize()
                 if world > 1:
                     dist.barrier()
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 e0.record()
-                r = parallel.root_parallel_search(eng, batch, n_sim, 0, 123, np.array([seed], np.uint32))
+                rp.run()                                          # reset + the whole search
                 e1.record()
                 torch.cuda.synchronize()
-            t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
-            if world > 1:
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            times.append(float(t.item()))
+                t = torch.tensor([e0.elapsed_time(e1)], device="cuda")
+                if world > 1:
+                    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                if rep > 0:
+                    best = float(t.item()) if best is None else min(best, float(t.item()))
+            r = rp.results()
+            rp.close()
+            times.append(best)
             depths.append(int(r["depth"][0]))
             rollouts += int(r["rollouts"][0])
             if r["solution_found"][0]:

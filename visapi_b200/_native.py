@@ -91,6 +91,7 @@ SYMBOLS = [
     ("bp_tree_check", C.c_int, [_vp, C.POINTER(C.c_int)]),
     ("bp_tree_root_counts", C.c_int, [_vp, _vp, _vp]),
     ("bp_tree_root_counts_dev", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_i64)]),
+    ("bp_tree_root_stats_dev", C.c_int, [_vp, C.POINTER(_vp), C.POINTER(_vp)]),
     ("bp_tree_destroy", C.c_int, [_vp]),
 ]
 
@@ -187,6 +188,22 @@ class _LockedLibrary(object):
         return locked
 
 
+class _StreamScope(object):
+    def __init__(self, engine, stream):
+        self.engine, self.stream, self.previous = engine, stream, None
+
+    def __enter__(self):
+        self.previous = self.engine.stream
+        if self.previous != self.stream:
+            self.engine.set_stream(self.stream)
+        return self.engine
+
+    def __exit__(self, *exc):
+        if self.previous != self.stream:
+            self.engine.set_stream(self.previous)
+        return False
+
+
 class Engine(object):
     """One bp_context: a device plus the stream its kernels run on.  Calls from several
     Python threads are serialised by a per-engine lock."""
@@ -203,6 +220,7 @@ class Engine(object):
             raise EngineError(msg)
         self._h = handle
         self.device = int(device)
+        self.stream = 0                  # the legacy NULL stream until set_stream
         if stream is not None:
             self.set_stream(stream)
 
@@ -222,8 +240,16 @@ class Engine(object):
             raise EngineError("rectpack_b200 error %d: %s" % (rc, self._lib.bp_last_error().decode()))
 
     def set_stream(self, cuda_stream):
-        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream)."""
+        """cuda_stream: integer cudaStream_t (e.g. torch.cuda.current_stream().cuda_stream); the
+        caller owns it and keeps it alive while the engine uses it.  Work already queued on the
+        previous stream is ordered before anything launched on the new one (bp_set_stream)."""
         self._check(self._lib.bp_set_stream(self._h, C.c_void_p(int(cuda_stream))))
+        self.stream = int(cuda_stream)
+
+    def on_stream(self, cuda_stream):
+        """Context manager: run the engine's kernels on ``cuda_stream`` inside the block (e.g.
+        torch's current stream, so that engine kernels and torch ops interleave in order)."""
+        return _StreamScope(self, int(cuda_stream))
 
     def synchronize(self):
         self._check(self._lib.bp_synchronize(self._h))
@@ -542,6 +568,12 @@ class Tree(object):
         n_nodes = np.zeros(self.B, np.int32)
         self.engine._check(self._lib.bp_tree_root_counts(self._h, _ptr(counts), _ptr(n_nodes)))
         return counts, n_nodes
+
+    def root_stats_dev(self):
+        """(counts pointer int32[B][E], Wsa pointer float64[B][E]) on the device."""
+        c, w = C.c_void_p(), C.c_void_p()
+        self.engine._check(self._lib.bp_tree_root_stats_dev(self._h, C.byref(c), C.byref(w)))
+        return c.value, w.value
 
     def root_counts_dev(self):
         ptr, nbytes = C.c_void_p(), C.c_int64()

@@ -28,6 +28,7 @@ def _arg(args, name, default=None):
 class Coach(object):
     def __init__(self, game, nnet, args, device=None):
         self.game, self.nnet, self.args, self.device = game, nnet, args, device
+        self.arena_results = []
         self.mcts = MCTS(self.game, self.nnet, self.args, device=device)
         self.trainExamplesHistory = []
         self.skipFirstSelfPlay = False
@@ -53,8 +54,11 @@ class Coach(object):
                 return [(x[0], x[1], x[2], r) for x in trainExamples]
 
     def learn(self):
-        """numIters x (numEps episodes of self-play, then nnet.train) (Coach.py:65-134).  The
-        reference accepts every new model (`if False:` at :122), so no arena is played."""
+        """numIters x (numEps episodes of self-play, then nnet.train) (Coach.py:65-134).  Like the
+        reference, the previous and the new net are pitted in the Arena for ``arenaCompare`` games
+        (:116-118) and the new model is accepted whatever the outcome (`if False:` at :122);
+        ``self.arena_results`` keeps the (prev wins, new wins, draws) of every iteration."""
+        self.arena_results = []
         losses = []
         for i in range(1, _arg(self.args, 'numIters', 1) + 1):
             if not self.skipFirstSelfPlay or i > 1:
@@ -69,11 +73,29 @@ class Coach(object):
                 self.saveTrainExamples(i - 1)
             examples = [e for part in self.trainExamplesHistory for e in part]
             shuffle(examples)
+            previous = self._snapshot_net()
             losses.append(self.nnet.train(examples))
+            n_arena = int(_arg(self.args, 'arenaCompare', 0) or 0)
+            if n_arena >= 2 and previous is not None:
+                from .arena import Arena, mcts_player
+                pmcts = MCTS(self.game, previous, self.args, device=self.device)
+                nmcts = MCTS(self.game, self.nnet, self.args, device=self.device)
+                for m in (pmcts, nmcts):
+                    m.predict_on_grid_only = False
+                arena = Arena(mcts_player(pmcts), mcts_player(nmcts), self.game)
+                self.arena_results.append(arena.playGames(n_arena))
             if ckpt:
                 self.nnet.save_checkpoint(folder=ckpt, filename=self.getCheckpointFile(i))
                 self.nnet.save_checkpoint(folder=ckpt, filename='best.pth.tar')
         return losses
+
+    def _snapshot_net(self):
+        """A frozen copy of the current net (the reference's pnet, Coach.py:19,109-111)."""
+        import copy
+        try:
+            return copy.deepcopy(self.nnet)
+        except Exception:
+            return None
 
     def getCheckpointFile(self, iteration):
         return 'checkpoint_' + str(iteration) + '.pth.tar'

@@ -334,7 +334,16 @@ int bp_destroy(bp_context* ctx)
 int bp_set_stream(bp_context* ctx, void* cuda_stream)
 {
     BP_REQUIRE(ctx != nullptr, "ctx is null");
-    ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+    cudaStream_t next = reinterpret_cast<cudaStream_t>(cuda_stream);
+    if (next == ctx->stream) return BP_OK;
+    // Work queued on the old stream may still use the context's scratch, arena or tree buffers:
+    // the new stream waits for it (an event, no host synchronisation).  The stream belongs to the
+    // caller and must be a stream of the context's device.
+    BP_CUDA(cudaSetDevice(ctx->device));
+    if (!ctx->fork_event) BP_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
+    BP_CUDA(cudaEventRecord(ctx->fork_event, ctx->stream));
+    BP_CUDA(cudaStreamWaitEvent(next, ctx->fork_event, 0));
+    ctx->stream = next;
     return BP_OK;
 }
 

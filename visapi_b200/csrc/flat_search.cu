@@ -817,10 +817,17 @@ int bp_search_max_depth(bp_search* s, int* max_depth)
     return BP_OK;
 }
 
-// AUTO: the form measured faster on B200
+// AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt):
+// the resident kernel when a depth of the whole batch is little work -- problems x 32-rollout
+// chunks per child <= 512 (one instance at any N up to 16 384, 125 problems at N = 100) -- where
+// the launch-per-depth form is a chain of launches with little in them; the launch-per-depth form
+// for big batches, whose playouts run ~6 % fewer instructions and share no SM with server warps.
+// A partitioned (root-parallel) search is resident: its exchange lives inside the kernel.
 static int default_mode(const bp_search* s)
 {
-    return BP_SEARCH_STEPPED;
+    if (!s->ring_cap) return BP_SEARCH_STEPPED;
+    if (s->p.n_ranks > 1) return BP_SEARCH_RESIDENT;
+    return (long long)s->p.n_problems * s->p.n_chunks <= 512 ? BP_SEARCH_RESIDENT : BP_SEARCH_STEPPED;
 }
 
 int bp_search_run(bp_search* s)

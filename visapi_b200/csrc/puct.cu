@@ -422,6 +422,19 @@ __global__ void tree_root_counts_kernel(TreeParams p, int32_t* __restrict__ coun
             root >= 0 ? p.nsa[((size_t)tree * p.cap + root) * p.n_entries + a] : 0;
 }
 
+// root statistics for the root-parallel merge: visit counts and value sums W = Q * N per action
+__global__ void tree_root_stats_kernel(TreeParams p, int32_t* __restrict__ counts, double* __restrict__ wsa)
+{
+    const int tree = blockIdx.x;
+    const int root = p.root[tree];
+    for (int a = threadIdx.x; a < p.n_entries; a += blockDim.x) {
+        const size_t e = ((size_t)tree * p.cap + (root >= 0 ? root : 0)) * p.n_entries + a;
+        const int n = root >= 0 ? p.nsa[e] : 0;
+        counts[(size_t)tree * p.n_entries + a] = n;
+        wsa[(size_t)tree * p.n_entries + a] = n > 0 ? __dmul_rn(p.qsa[e], (double)n) : 0.0;
+    }
+}
+
 }  // namespace bp
 
 // ================================================================== host side
@@ -441,6 +454,7 @@ struct bp_tree {
     double* d_values = nullptr;
     double* d_out_value = nullptr;
     int32_t* d_counts = nullptr;
+    double* d_wsa = nullptr;
     uint32_t* d_root_occ = nullptr;
     uint8_t* d_root_tiles = nullptr;
 };
@@ -528,6 +542,7 @@ int bp_tree_create(bp_context* ctx, int n_trees, int rows, int cols, int n_entri
     TRY(tree_alloc(t, &t->d_values, B));
     TRY(tree_alloc(t, &t->d_out_value, B));
     TRY(tree_alloc(t, &t->d_counts, B * E));
+    TRY(tree_alloc(t, &t->d_wsa, B * E));
     TRY(tree_alloc(t, &t->d_root_occ, B * rows * p.wpr));
     TRY(tree_alloc(t, &t->d_root_tiles, B * E * 2));
 #undef TRY
@@ -686,6 +701,21 @@ int bp_tree_root_counts_dev(bp_tree* t, void** counts_dev, int64_t* n_bytes)
     BP_CUDA(cudaGetLastError());
     *counts_dev = t->d_counts;
     *n_bytes = (int64_t)p.n_trees * p.n_entries * 4;
+    return BP_OK;
+}
+
+/* visit counts Nsa (int32[n_trees][n_entries]) and value sums Wsa = Qsa * Nsa
+ * (float64[n_trees][n_entries]) of the roots, left on the device */
+int bp_tree_root_stats_dev(bp_tree* t, void** counts_dev, void** wsa_dev)
+{
+    BP_REQUIRE(t && counts_dev && wsa_dev, "null argument");
+    BP_CUDA(cudaSetDevice(t->ctx->device));
+    const TreeParams& p = t->p;
+    tree_root_stats_kernel<<<p.n_trees, 128, 0, t->ctx->stream>>>(p, t->d_counts, t->d_wsa);
+    t->ctx->launches++;
+    BP_CUDA(cudaGetLastError());
+    *counts_dev = t->d_counts;
+    *wsa_dev = t->d_wsa;
     return BP_OK;
 }
 

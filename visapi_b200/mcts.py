@@ -70,7 +70,12 @@ class CustomMCTS(object):
     # ------------------------------------------------------------------ a12 predict
     def predict(self, temp=1, N=3000):
         """-> (root State, depth, solution_found); sets n_tiles_placed and
-        solution_tiles_order exactly as the reference (occupancy = non-zero cells)."""
+        solution_tiles_order as the reference does WITH ITS OCCUPANCY BUG FIXED: a cell is occupied
+        iff it is non-zero.  The reference's predict() paints committed tiles with 1, 2, 3, ... but
+        tests placements with colorful_states=False ("== 1" only, binpack/MCTS.py:59 ->
+        engine/solution_checker.py:117-119), so from depth 2 on the as-shipped code can lay a tile
+        over cells painted >= 2; depth, score and n_tiles_placed then differ from this class on
+        such instances (tests/golden/as_shipped.json)."""
         board = np.asarray(self.state.board)
         tiles = _as_tile_tuples(self.state.tiles)
         eng = runtime.get_engine(self.device)
@@ -78,7 +83,9 @@ class CustomMCTS(object):
         res = eng.flat_search(
             [board.shape[0]], [board.shape[1]], pack_tiles([tiles], len(tiles) + len(tiles) % 2),
             [len(tiles)], int(N), strat, self.seed, [self.stream],
-            boards=pack_occupancy(board[None], colorful=True), want_scores=True)
+            # an empty board needs no upload and lets the engine take its lane-per-rollout kernels
+            boards=pack_occupancy(board[None], colorful=True) if board.any() else None,
+            want_scores=True)
         depth = int(res["depth"][0])
         found = bool(res["solution_found"][0])
         self.n_tiles_placed = int(res["n_tiles_placed"][0])

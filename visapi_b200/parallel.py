@@ -52,6 +52,32 @@ def merge_child_stats(per_rank):
     return out
 
 
+def allreduce_root_stats(counts, wsa, group=None):
+    """Root-parallel PUCT: every rank searched its own trees from the same
+    roots; the root visit counts Nsa and value sums Wsa = Qsa * Nsa of all ranks are summed in
+    place (torch tensors on any device) before the policy is formed from the counts
+    (binpack/MCTS.py:221-244).  Returns (counts, wsa, q) with q = wsa / counts (0 where unvisited)."""
+    import torch
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(counts, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(wsa, op=dist.ReduceOp.SUM, group=group)
+    q = torch.where(counts > 0, wsa / counts.clamp(min=1).to(wsa.dtype), torch.zeros_like(wsa))
+    return counts, wsa, q
+
+
+def probs_from_counts(counts, temp=1):
+    """MCTS.getActionProb's policy (binpack/MCTS.py:236-244) from (summed) visit counts [B, E]."""
+    counts = np.asarray(counts, dtype=np.float64)
+    if temp == 0:
+        probs = np.zeros_like(counts)
+        probs[np.arange(counts.shape[0]), counts.argmax(axis=1)] = 1
+        return probs
+    c = counts ** (1. / temp)
+    total = c.sum(axis=1, keepdims=True)
+    return np.divide(c, total, out=np.zeros_like(c), where=total > 0)
+
+
 class _DevicePointer(object):
     """Exposes a raw device pointer through __cuda_array_interface__ (for torch.as_tensor)."""
 
@@ -60,15 +86,23 @@ class _DevicePointer(object):
                                          "data": (int(ptr), False), "version": 2}
 
 
-class ResidentRootParallel(object):
-    """A root-parallel search kept across runs: partition, peer-memory exchange buffers (CUDA IPC
-    handles swapped once over torch.distributed), then ``run()`` = reset + ONE resident kernel
-    launch per rank.  Every rank must construct, run and close it together."""
+class RootParallelSearch(object):
+    """A root-parallel flat search kept across runs.  Every rank must construct it, ``run()`` it
+    and ``close()`` it together, on the CUDA stream the engine was given.
 
-    def __init__(self, engine, batch, n_sim, strategy, seed, streams=None, group=None):
+    exchange="resident": partition + peer-memory exchange buffers (CUDA IPC handles swapped once
+    over torch.distributed); ``run()`` = reset + ONE resident kernel launch per rank, the
+    per-move merge happens inside the kernels over NVLink.
+    exchange="nccl": launch-per-depth kernels with one ``all_gather_into_tensor`` per move."""
+
+    def __init__(self, engine, batch, n_sim, strategy, seed, streams=None, group=None,
+                 exchange="resident"):
         import torch
         import torch.distributed as dist
 
+        if exchange not in ("resident", "nccl"):
+            raise ValueError("exchange must be 'resident' or 'nccl'")
+        self.exchange = exchange
         self.group = group
         self.dist = dist if dist.is_initialized() else None
         world = dist.get_world_size(group) if self.dist else 1
@@ -76,20 +110,38 @@ class ResidentRootParallel(object):
         self.world, self.rank = world, rank
         self.search = engine.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"],
                                     n_sim, strategy, seed, streams)
-        self.search.set_mode("resident")
-        if world > 1:
-            begin, n_local = split_sims(n_sim, rank, world)
+        begin, n_local = split_sims(n_sim, rank, world)
+        if exchange == "resident":
+            self.search.set_mode("resident")
+            if world > 1:
+                self.search.set_partition(rank, world, begin, n_local)
+                handle, _ = self.search.exchange_create()
+                mine = torch.from_numpy(handle).cuda()
+                every = torch.empty(world * 64, dtype=torch.uint8, device=mine.device)
+                dist.all_gather_into_tensor(every, mine, group=group)
+                self.search.exchange_connect(ipc_handles=every.cpu().numpy().reshape(world, 64))
+                dist.barrier(group=group)
+        else:
+            self.search.set_mode("stepped")
             self.search.set_partition(rank, world, begin, n_local)
-            handle, _ = self.search.exchange_create()
-            mine = torch.from_numpy(handle).cuda()
-            every = torch.empty(world * 64, dtype=torch.uint8, device=mine.device)
-            dist.all_gather_into_tensor(every, mine, group=group)
-            self.search.exchange_connect(ipc_handles=every.cpu().numpy().reshape(world, 64))
-            dist.barrier(group=group)
+            ptr, nbytes = self.search.stats_buffer()
+            self._local = torch.as_tensor(_DevicePointer(ptr, nbytes), device="cuda")
+            self._gathered = torch.empty(world * nbytes, dtype=torch.uint8, device=self._local.device)
 
     def run(self):
-        self.search.reset()
-        self.search.run()
+        s = self.search
+        s.reset()
+        if self.exchange == "resident":
+            s.run()
+            return
+        for _ in range(s.max_depth):
+            s.step_rollouts()
+            s.step_reduce()
+            if self.world > 1:
+                self.dist.all_gather_into_tensor(self._gathered, self._local, group=self.group)
+            else:
+                self._gathered.copy_(self._local)
+            s.step_commit(self._gathered.data_ptr())
 
     def results(self, want_scores=False):
         return self.search.results(want_scores=want_scores)
@@ -109,36 +161,9 @@ def root_parallel_search(engine, batch, n_sim, strategy, seed, streams=None, gro
     """Flat search of ``batch`` (datasets.batch_arrays) with the rollouts of every child split
     over the ranks of ``group``.  Must be called by every rank, on the CUDA stream the engine
     was given (torch's current stream).  Returns the same dict as Engine.flat_search."""
-    import torch
-    import torch.distributed as dist
-
-    world = dist.get_world_size(group) if dist.is_initialized() else 1
-    rank = dist.get_rank(group) if dist.is_initialized() else 0
-    if exchange == "resident":
-        rp = ResidentRootParallel(engine, batch, n_sim, strategy, seed, streams, group)
-        try:
-            rp.run()
-            return rp.results(want_scores=want_scores)
-        finally:
-            rp.close()
-    search = engine.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim,
-                           strategy, seed, streams)
+    rp = RootParallelSearch(engine, batch, n_sim, strategy, seed, streams, group, exchange)
     try:
-        begin, n_local = split_sims(n_sim, rank, world)
-        search.set_partition(rank, world, begin, n_local)
-        search.reset()
-        ptr, nbytes = search.stats_buffer()
-        local = torch.as_tensor(_DevicePointer(ptr, nbytes), device="cuda")
-        gathered = torch.empty(world * nbytes, dtype=torch.uint8, device=local.device)
-        for _ in range(search.max_depth):
-            search.step_rollouts()
-            search.step_reduce()
-            if world > 1:
-                dist.all_gather_into_tensor(gathered, local, group=group)
-            else:
-                gathered.copy_(local)
-            search.step_commit(gathered.data_ptr())
-        res = search.results(want_scores=want_scores)
+        rp.run()
+        return rp.results(want_scores=want_scores)
     finally:
-        search.close()
-    return res
+        rp.close()

@@ -168,6 +168,15 @@ class BatchedMCTS(object):
         B, H, W, E = self.B, self.height, self.width, self.n_actions
         wpr = (W + 31) // 32
         shifts = None
+        # The select / backup kernels and the torch ops between them (bit unpacking, the net) must
+        # run on ONE stream: the engine is bound to torch's current stream for the duration, so the
+        # loop is also correct under torch.cuda.stream(...) and the temporaries the net returns are
+        # not recycled by the caching allocator before the backup kernel has read them.
+        with self._tree.engine.on_stream(torch.cuda.current_stream(
+                torch.device("cuda", self._tree.engine.device)).cuda_stream):
+            self._simulate_on_device(predict_dev, n, torch, _DevicePointer, B, H, W, E, wpr, shifts)
+
+    def _simulate_on_device(self, predict_dev, n, torch, _DevicePointer, B, H, W, E, wpr, shifts):
         for _ in range(self.num_sims if n is None else n):
             occ_p, tiles_p, _valid_p, _status_p = self._tree.select_dev()
             if shifts is None:
@@ -197,6 +206,22 @@ class BatchedMCTS(object):
 
     def root_counts_dev(self):
         return self._tree.root_counts_dev()
+
+    def action_probs_root_parallel(self, temp=1, group=None):
+        """Root-parallel form of ``action_probs``: the root Nsa and Wsa of every rank's trees are
+        all-reduced (SUM, NCCL over NVLink, on the device buffers) and the policy is formed from
+        the summed counts.  Every rank must call it, on the engine's stream; without an
+        initialised process group it equals ``action_probs``.  -> (probs [B, E], q [B, E])."""
+        import torch
+        from .parallel import _DevicePointer, allreduce_root_stats, probs_from_counts
+        B, E = self.B, self.n_actions
+        dev = torch.device("cuda", self._tree.engine.device)
+        with self._tree.engine.on_stream(torch.cuda.current_stream(dev).cuda_stream):
+            c_ptr, w_ptr = self._tree.root_stats_dev()
+            counts = torch.as_tensor(_DevicePointer(c_ptr, B * E * 4), device=dev).view(torch.int32).view(B, E)
+            wsa = torch.as_tensor(_DevicePointer(w_ptr, B * E * 8), device=dev).view(torch.float64).view(B, E)
+            counts, wsa, q = allreduce_root_stats(counts, wsa, group)
+            return probs_from_counts(counts.cpu().numpy(), temp), q.cpu().numpy()
 
     def reset(self):
         self._tree.reset()

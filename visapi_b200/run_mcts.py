@@ -162,15 +162,40 @@ class _NpEncoder(json.JSONEncoder):
         return super(_NpEncoder, self).default(obj)
 
 
+def ascii_tree(nested):
+    """The text the reference writes next to every result (run_mcts.py:268-279:
+    ``asciitree.LeftAligned()(tree)`` on ``State.render_children()``), restated from asciitree
+    0.3.3's LeftAligned drawer with its default BoxStyle (ASCII glyphs, horizontal length 2,
+    indent 1, one space before the label): children hang under their parent as `` +-- label``,
+    open levels continue with `` |   ``."""
+    (label, children), = nested.items()
+
+    def render(node_label, node_children):
+        lines = [str(node_label)]
+        items = list(node_children.items())
+        for i, (lab, sub) in enumerate(items):
+            last = i == len(items) - 1
+            child = render(lab, sub)
+            lines.append(" +-- " + child[0])
+            lines.extend((("     " if last else " |   ") + line) for line in child[1:])
+        return lines
+    return "\n".join(render(label, children))
+
+
 def dump_trees(options, probs, strategies, device):
-    """One JSON file per (problem, strategy) with the tree CustomMCTS.predict builds: every
-    evaluated child of every depth with its score and board (run_mcts.py:227-239)."""
+    """Per (problem, strategy): the tree CustomMCTS.predict builds as JSON (every evaluated child
+    of every depth with its score and board, run_mcts.py:227-239) and as the ascii tree text
+    (run_mcts.py:268-279)."""
     os.makedirs(options["dump_tree"], exist_ok=True)
     for i, p in enumerate(probs):
         for strategy in strategies:
             m = CustomMCTS(p.entries(), p.board(), strategy=strategy, seed=options["seed"], stream=i,
                            device=device)
             root, depth, found = m.predict(N=options["n_sim"])
+            text = ascii_tree(root.render_children(only_ids=False)[0])
+            with open(os.path.join(options["dump_tree"], "%d_%d_%d_%s_%d_%d.txt" % (
+                    len(p.tiles), p.cols, p.rows, strategy, options["n_sim"], i)), "w") as f:
+                f.write(text)
             root.centralize_node_with_children()
             name = "%d_%d_%d_%s_%d_%d_tree.json" % (len(p.tiles), p.cols, p.rows, strategy,
                                                     options["n_sim"], i)
