@@ -199,3 +199,40 @@ def test_cli_instance_loading():
     probs = run_mcts.load_instances(opts)
     assert len(probs) == 3 and all((p.rows, p.cols, len(p.tiles)) == (6, 7, 8) for p in probs)
     assert all(sum(h * w for h, w in p.tiles) == 42 for p in probs)
+
+
+def test_cli_reports_instances_outside_the_engine_limits(tmp_path, capsys, monkeypatch):
+    """A 129-column instance (puzzles_n20_with_solutions_2.csv has one, 129 x 67) is reported and
+    skipped by the command before any device call; with nothing left the command returns."""
+    from visapi_b200 import datasets, run_mcts
+    big = datasets.Problem(67, 129, [(67, 129)], "too-wide")
+    monkeypatch.setattr(run_mcts, "load_instances", lambda options: [big])
+    monkeypatch.setattr(run_mcts.runtime, "set_default_device", lambda device: None)
+    out = run_mcts.run_mcts({"device": "cuda:0", "n_tiles": 1, "both_strategies": False, "avg_depth": False,
+                             "n_sim": 5, "seed": 123, "quiet": True, "out": None, "dump_tree": None})
+    assert out == []
+    text = capsys.readouterr().out
+    assert "skipped 1 instance" in text and "67x129" in text
+
+
+def test_ascii_tree_is_asciitree_left_aligned():
+    """run_mcts.py:268-279 writes asciitree.LeftAligned()(tree); asciitree (0.3.3, not installed
+    here) documents its output with this example, which the restatement must reproduce."""
+    from collections import OrderedDict as OD
+    from visapi_b200.run_mcts import ascii_tree
+    tree = {"asciitree": OD([("sometimes", OD([("you", {})])),
+                             ("just", OD([("want", OD([("to", {}), ("draw", {})]))])),
+                             ("trees", {}),
+                             ("in", OD([("your", OD([("terminal", {})]))]))])}
+    assert ascii_tree(tree) == "\n".join([
+        "asciitree",
+        " +-- sometimes",
+        " |   +-- you",
+        " +-- just",
+        " |   +-- want",
+        " |       +-- to",
+        " |       +-- draw",
+        " +-- trees",
+        " +-- in",
+        "     +-- your",
+        "         +-- terminal"])

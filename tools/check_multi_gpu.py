@@ -31,11 +31,13 @@ def main():
             single = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"],
                                      n_sim, strategy, 123, np.arange(len(probs), dtype=np.uint32),
                                      want_scores=True)
-            rp = parallel.root_parallel_search(eng, batch, n_sim, strategy, 123,
-                                               np.arange(len(probs), dtype=np.uint32), want_scores=True)
-            for k in ("depth", "solution_found", "n_tiles_placed", "rollouts", "rollout_placements",
-                      "n_order", "order", "path", "child_scores"):
-                assert np.array_equal(single[k], rp[k]), (strategy, n_sim, k)
+            for exchange in ("resident", "nccl"):     # in-kernel peer-memory exchange / NCCL all-gather
+                rp = parallel.root_parallel_search(eng, batch, n_sim, strategy, 123,
+                                                   np.arange(len(probs), dtype=np.uint32), want_scores=True,
+                                                   exchange=exchange)
+                for k in ("depth", "solution_found", "n_tiles_placed", "rollouts", "rollout_placements",
+                          "n_order", "order", "path", "child_scores"):
+                    assert np.array_equal(single[k], rp[k]), (exchange, strategy, n_sim, k)
             # instance-parallel: my shard, compared with the same rows of the full run
             mine = parallel.shard_indices(len(probs), rank, world)
             sub = datasets.batch_arrays([probs[i] for i in mine], entry_stride=batch["tiles"].shape[1])

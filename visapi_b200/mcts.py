@@ -142,10 +142,12 @@ class CustomMCTS(object):
         child.children = [node]
         for mv in moves:
             val += 1
+            # the rollout plays with destroy_state=True (MCTS.py:175-178): the state it moves FROM
+            # is painted in place, and its successor starts as a copy of that board -- so in the
+            # rendered chain every node already shows the tile that leads to its child
             pos = _first_free(node.board)
-            nb = np.copy(node.board)
-            nb[pos[0]: pos[0] + mv[0], pos[1]: pos[1] + mv[1]] = val
-            nxt = State(board=nb, tiles=SolutionChecker.eliminate_pair_tiles(node.tiles, mv),
+            node.board[pos[0]: pos[0] + mv[0], pos[1]: pos[1] + mv[1]] = val
+            nxt = State(board=node.board, tiles=SolutionChecker.eliminate_pair_tiles(node.tiles, mv),
                         parent=node)
             node.score = len(node.tiles) / ORIENTATIONS - 1
             node.children.append(nxt)

@@ -29,6 +29,10 @@ from .verify import replay_solution
 ORIENTATIONS = 2
 
 
+MAX_SIDE = 128          # BP_MAX_ROWS / BP_MAX_COLS of include/rectpack_b200.h
+MAX_ENTRIES = 128       # BP_MAX_ENTRIES
+
+
 def add_arguments(parser):
     parser.add_argument("n_tiles", type=int, help="number of tiles")
     parser.add_argument("rows", type=int, help="number of rows")
@@ -90,6 +94,16 @@ def run_mcts(options):
     runtime.set_default_device(device)
 
     probs = load_instances(options)
+    # The engine holds a board as <= 128 rows of <= 128 columns (four 32-bit words per row or bit
+    # plane) and <= 128 tile entries.  Larger instances are reported and skipped, never silently
+    # altered: 1 of the 1615 instances of puzzles_n20_with_solutions_2.csv (129 x 67) is outside.
+    too_big = [p for p in probs if p.rows > MAX_SIDE or p.cols > MAX_SIDE or 2 * len(p.tiles) > MAX_ENTRIES]
+    if too_big:
+        probs = [p for p in probs if p not in too_big]
+        if rank == 0:
+            print("skipped %d instance(s) outside the engine's limits (rows, cols <= %d; tiles <= %d): %s"
+                  % (len(too_big), MAX_SIDE, MAX_ENTRIES // 2,
+                     ", ".join("%dx%d/%d tiles" % (p.rows, p.cols, len(p.tiles)) for p in too_big[:8])))
     if not probs:
         print("no instance with %d tiles" % options["n_tiles"])
         return []
@@ -176,10 +190,11 @@ def ascii_tree(nested):
         for i, (lab, sub) in enumerate(items):
             last = i == len(items) - 1
             child = render(lab, sub)
-            lines.append(" +-- " + child[0])
-            lines.extend((("     " if last else " |   ") + line) for line in child[1:])
+            lines.append("+-- " + child[0])
+            lines.extend((("    " if last else "|   ") + line) for line in child[1:])
         return lines
-    return "\n".join(render(label, children))
+    out = render(label, children)
+    return "\n".join([out[0]] + [" " + line for line in out[1:]])
 
 
 def dump_trees(options, probs, strategies, device):
