@@ -104,11 +104,12 @@ struct bp_search {
     std::vector<ProblemDesc> h_desc;
     // class bookkeeping
     std::vector<int> classes;                   // classes present
-    int cls_count[FS_CLASSES] = {0};
-    int cls_prob_off[FS_CLASSES] = {0};          // offset into d_cls_problems
-    int cls_list_off[FS_CLASSES] = {0};          // offset into child_list
-    int grid_rollout[FS_CLASSES] = {0};
-    int grid_lanes[FS_CLASSES] = {0};
+    // indexed by CHAIN (class + FS_CLASSES * sub-chain); `classes` lists the chains present
+    std::vector<int> cls_count = std::vector<int>(FS_CHAINS, 0);
+    std::vector<int> cls_prob_off = std::vector<int>(FS_CHAINS, 0);    // offset into d_cls_problems
+    std::vector<int> cls_list_off = std::vector<int>(FS_CHAINS, 0);    // offset into child_list
+    std::vector<int> grid_rollout = std::vector<int>(FS_CHAINS, 0);
+    std::vector<int> grid_lanes = std::vector<int>(FS_CHAINS, 0);
     int* d_cls_problems = nullptr;
     ProblemDesc* d_desc = nullptr;
     uint32_t* d_init_occ = nullptr;            // initial boards (NULL: empty boards)
@@ -132,6 +133,11 @@ struct bp_search {
     std::vector<cudaEvent_t> cls_done;
     std::vector<int> cls_depth;
     cudaEvent_t fork_ev = nullptr;
+    // the forked launch-per-depth run captured once as a CUDA graph (from the second run on): one
+    // graph launch replaces ~2 x depths x chains kernel launches and their stream fork / join
+    cudaGraphExec_t graph_exec = nullptr;
+    int graph_launches = 0;                     // kernel nodes in the graph
+    int n_runs = 0;
     // resident search (one launch runs every depth of every problem): queue, ring, variant
     int mode = BP_SEARCH_AUTO;
     bool ran_resident = false;
@@ -174,6 +180,7 @@ int bp_search_destroy(bp_search* s)
     if (!s) return BP_OK;
     cudaSetDevice(s->ctx->device);
     cudaStreamSynchronize(s->ctx->stream);
+    if (s->graph_exec) cudaGraphExecDestroy(s->graph_exec);
     for (void* mapped : s->peer_opened) cudaIpcCloseMemHandle(mapped);
     if (s->d_exchange) cudaFree(s->d_exchange);
     if (s->arena_from_ctx) s->ctx->arena_busy = false;
@@ -223,7 +230,8 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     s->max_depth = max_n;
 
     s->h_desc.resize(n_problems);
-    std::vector<std::vector<int>> by_class(FS_CLASSES);
+    std::vector<std::vector<int>> by_class(FS_CHAINS);
+    std::vector<int> class_seen(FS_CLASSES, 0);
     for (int i = 0; i < n_problems; ++i) {
         ProblemDesc& d = s->h_desc[i];
         d.rows = rows[i]; d.cols = cols[i]; d.n_entries = n_entries[i];
@@ -236,12 +244,31 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         d.cls = (nb - 5 + three_words) * N_CLASSES + shape_class(rows_of_class, cols[i], n_entries[i]);
         d.stream = streams ? streams[i] : (uint32_t)i;
         d.pad0 = d.pad1 = d.pad2 = 0;
-        by_class[d.cls].push_back(i);
+        class_seen[d.cls]++;
+    }
+    // sub-chains per class: a batch too small to fill the GPU with one launch sequence per class
+    // gets several (problems dealt round-robin), so that about 8 sequences are in flight
+    int n_present = 0;
+    for (int c = 0; c < FS_CLASSES; ++c) n_present += class_seen[c] ? 1 : 0;
+    int subs = 1;
+    // (measured on B200, profiles/r2/shard_sweep_chains.txt: 1 / 2 / 4 / 8 chains per class take
+    // 2.09 / 2.19 / 2.27 / 3.6 ms on a 125-problem shard and 11.28 / 11.63 / 12.17 / 13.36 ms on the
+    // full set -- every extra launch sequence costs more in launches than its overlap returns, so
+    // one chain per class is the default and BP_SUBCHAINS only an experiment knob)
+    (void)n_present;
+    if (const char* env = getenv("BP_SUBCHAINS")) subs = std::max(1, std::min(FS_MAX_SUBCHAINS, atoi(env)));
+    {
+        std::vector<int> dealt(FS_CLASSES, 0);
+        for (int i = 0; i < n_problems; ++i) {
+            const int c = s->h_desc[i].cls;
+            const int k = std::min(subs, std::max(1, class_seen[c] / 4));     // at least ~4 problems per chain
+            by_class[c + FS_CLASSES * (dealt[c]++ % k)].push_back(i);
+        }
     }
 
     std::vector<int> cls_problems;
     int list_off = 0;
-    for (int c = 0; c < FS_CLASSES; ++c) {
+    for (int c = 0; c < FS_CHAINS; ++c) {
         s->cls_count[c] = (int)by_class[c].size();
         s->cls_prob_off[c] = (int)cls_problems.size();
         s->cls_list_off[c] = list_off;
@@ -335,9 +362,9 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         TRY(dev_alloc(s, &p.order, P * (p.es / 2 + 2) * 2));
         s->res_end = mark();
         TRY(dev_alloc(s, &p.prev_tile, P));
-        s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * FS_CLASSES * sizeof(unsigned);
-        TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * FS_CLASSES));
-        TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * FS_CLASSES));
+        s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * FS_CHAINS * sizeof(unsigned);
+        TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS));
+        TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS));
         if (p.use_lanes) TRY(dev_alloc(s, &p.pending, P));
         if (!boards) TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));       // empty boards: zeroed too
         s->zero_end = mark();
@@ -419,7 +446,8 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     BP_CUDA(cudaStreamSynchronize(ctx->stream));
 
     // persistent grid per class: every SM filled to the occupancy limit of that kernel
-    for (int c : s->classes) {
+    for (int chain : s->classes) {
+        const int c = chain % FS_CLASSES;
         if (!ctx->occ_rollout[c]) {
             int per_sm = 1;
             dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
@@ -429,7 +457,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             });
             ctx->occ_rollout[c] = std::max(per_sm, 1);
         }
-        s->grid_rollout[c] = ctx->sm_count * ctx->occ_rollout[c];
+        s->grid_rollout[chain] = ctx->sm_count * ctx->occ_rollout[c];
         if (p.use_lanes) {
             if (!ctx->occ_lanes[c]) {
                 int per_sm_l = 1;
@@ -441,7 +469,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
                 });
                 ctx->occ_lanes[c] = std::max(per_sm_l, 1);
             }
-            s->grid_lanes[c] = ctx->sm_count * ctx->occ_lanes[c];
+            s->grid_lanes[chain] = ctx->sm_count * ctx->occ_lanes[c];
         }
     }
     if (s->ring_cap) {
@@ -472,8 +500,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         s->cls_done.push_back(e);
         const int c = s->classes[k];
         int md = 0;
-        for (int i = 0; i < n_problems; ++i)
-            if (s->h_desc[i].cls == c) md = std::max(md, s->h_desc[i].n_entries / 2);
+        for (int i : by_class[c]) md = std::max(md, s->h_desc[i].n_entries / 2);
         s->cls_depth.push_back(md);
     }
     *out = s;
@@ -504,6 +531,7 @@ int bp_search_set_partition(bp_search* s, int rank, int n_ranks, int sim_begin, 
     s->p.sim_begin = sim_begin;
     s->p.n_local = n_local;
     s->p.n_chunks = std::max(1, (n_local + CHUNK - 1) / CHUNK);
+    if (s->graph_exec) { cudaGraphExecDestroy(s->graph_exec); s->graph_exec = nullptr; }   // parameters are baked in
     s->ready = false;
     return BP_OK;    // the record buffer was sized for all n_sim rollouts
 }
@@ -592,7 +620,7 @@ static void launch_advance_class(bp_search* s, int c, int next_slot, const Child
 {
     const int n = s->cls_count[c];
     const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
-    dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
+    dispatch_class((c % FS_CLASSES) % N_CLASSES, [&](auto R, auto Wc, auto E) {
         fs_advance_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value, FIRST>
             <<<grid, ADV_WARPS * 32, 0, st>>>(s->p, c, s->cls_list_off[c],
                                               s->d_cls_problems + s->cls_prob_off[c], n, next_slot,
@@ -619,13 +647,25 @@ static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t s
 {
     int upw = overlapped ? 1 : 16;                            // in half units: 0.5 / 8 units per warp
     if (const char* env = getenv("BP_UNITS_PER_WARP")) upw = std::max(1, (int)(2.0 * atof(env) + 0.5));
-    if (s->p.use_lanes)
-        dispatch_lanes(c, [&](auto NBc, auto Wc, auto E) {
+    if (s->p.use_lanes) {
+        // no more blocks than the units this depth can have: every problem of the chain has at most
+        // (entries - 2 depth) children, and a launch is cut into about n_warps * upw / 2 units when
+        // the children are fewer than that (see the kernel) -- a full grid of blocks that find the
+        // counter exhausted costs the launch several microseconds on every SM
+        const int full = s->grid_lanes[c];
+        const long long children = (long long)s->cls_count[c] * std::max(0, s->p.es - 2 * depth);
+        const long long units = std::min<long long>(children * s->p.n_chunks,
+                                                    children + ((long long)full * 4 * upw) / 2);
+        static const bool shrink = !(getenv("BP_SHRINK_GRID") && atoi(getenv("BP_SHRINK_GRID")) == 0);
+        const int grid = shrink ? (int)std::max<long long>(s->ctx->sm_count, std::min<long long>(full, (units + 3) / 4))
+                                : full;
+        dispatch_lanes(c % FS_CLASSES, [&](auto NBc, auto Wc, auto E) {
             fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>
-                <<<s->grid_lanes[c], 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth, upw);
+                <<<grid, 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth, upw, full * 4);
         });
+    }
     else
-        dispatch_class(c % N_CLASSES, [&](auto R, auto Wc, auto E) {
+        dispatch_class((c % FS_CLASSES) % N_CLASSES, [&](auto R, auto Wc, auto E) {
             fs_rollout_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value>
                 <<<s->grid_rollout[c], 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth);
         });
@@ -730,7 +770,7 @@ int bp_search_step_reduce(bp_search* s)
     for (int c : s->classes) {
         const int n = s->cls_count[c];
         const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
-        const int ej = (c % N_CLASSES) % 3 == 0 ? 1 : ((c % N_CLASSES) % 3 == 1 ? 2 : 4);
+        const int ej = ((c % FS_CLASSES) % N_CLASSES) % 3 == 0 ? 1 : (((c % FS_CLASSES) % N_CLASSES) % 3 == 1 ? 2 : 4);
         const int* list = s->d_cls_problems + s->cls_prob_off[c];
         if (ej == 1) fs_reduce_kernel<1><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
         else if (ej == 2) fs_reduce_kernel<2><<<grid, ADV_WARPS * 32, 0, s->ctx->stream>>>(s->p, list, n);
@@ -904,24 +944,60 @@ int bp_search_run(bp_search* s)
         set_error("bp_search_run: call bp_search_reset first");
         return BP_ERR_STATE;
     }
-    // fork: every class runs its whole depth loop on its own stream, then join.  Launches are
-    // issued depth-major (all classes' depth 0, then depth 1, ...) so that every chain starts
+    // fork: every chain runs its whole depth loop on its own stream, then join.  Launches are
+    // issued depth-major (all chains' depth 0, then depth 1, ...) so that every chain starts
     // at once instead of waiting for the host to issue the chains before it.
     BP_CUDA(cudaSetDevice(s->ctx->device));
-    BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
-    for (size_t k = 0; k < s->classes.size(); ++k)
-        BP_CUDA(cudaStreamWaitEvent(s->cls_stream[k], s->fork_ev, 0));
-    for (int d = 0; d < s->max_depth; ++d) {
-        for (size_t k = 0; k < s->classes.size(); ++k) {
-            if (d >= s->cls_depth[k]) continue;
-            launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true);
-            launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
+    auto issue = [&]() -> int {
+        BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
+        for (size_t k = 0; k < s->classes.size(); ++k)
+            BP_CUDA(cudaStreamWaitEvent(s->cls_stream[k], s->fork_ev, 0));
+        for (int d = 0; d < s->max_depth; ++d) {
+            for (size_t k = 0; k < s->classes.size(); ++k) {
+                if (d >= s->cls_depth[k]) continue;
+                launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true);
+                launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
+            }
         }
-    }
-    BP_CUDA(cudaGetLastError());
-    for (size_t k = 0; k < s->classes.size(); ++k) {
-        BP_CUDA(cudaEventRecord(s->cls_done[k], s->cls_stream[k]));
-        BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->cls_done[k], 0));
+        BP_CUDA(cudaGetLastError());
+        for (size_t k = 0; k < s->classes.size(); ++k) {
+            BP_CUDA(cudaEventRecord(s->cls_done[k], s->cls_stream[k]));
+            BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->cls_done[k], 0));
+        }
+        return BP_OK;
+    };
+    // From the second run of a search on, the whole fork / launch / join sequence is one CUDA
+    // graph: its launch parameters never change between resets (a one-shot search never pays for
+    // the capture).  BP_GRAPH=0 keeps plain launches; the legacy NULL stream cannot be captured.
+    static const bool graph_ok = !(getenv("BP_GRAPH") && atoi(getenv("BP_GRAPH")) == 0);
+    s->n_runs++;
+    if (graph_ok && s->ctx->stream != nullptr && (s->n_runs >= 2 || s->graph_exec)) {
+        if (!s->graph_exec) {
+            const int64_t before = s->ctx->launches;
+            cudaGraph_t graph = nullptr;
+            BP_CUDA(cudaStreamBeginCapture(s->ctx->stream, cudaStreamCaptureModeThreadLocal));
+            const int rc = issue();
+            const cudaError_t end = cudaStreamEndCapture(s->ctx->stream, &graph);
+            s->graph_launches = (int)(s->ctx->launches - before);
+            s->ctx->launches = before;
+            if (rc || end != cudaSuccess || !graph) {
+                if (graph) cudaGraphDestroy(graph);
+                set_error("CUDA graph capture of the search failed: %s", cudaGetErrorString(end));
+                return BP_ERR_CUDA;
+            }
+            const cudaError_t inst = cudaGraphInstantiate(&s->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            if (inst != cudaSuccess) {
+                s->graph_exec = nullptr;
+                set_error("cudaGraphInstantiate failed: %s", cudaGetErrorString(inst));
+                return BP_ERR_CUDA;
+            }
+        }
+        BP_CUDA(cudaGraphLaunch(s->graph_exec, s->ctx->stream));
+        s->ctx->launches += s->graph_launches;
+    } else {
+        const int rc = issue();
+        if (rc) return rc;
     }
     s->cur_depth = s->max_depth;
     return BP_OK;

@@ -15,9 +15,9 @@ __global__ void __launch_bounds__(128)
 fs_rollout_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot)
 {
     const int lane = lane_id();
-    const unsigned n_children = p.child_count[depth_slot * FS_CLASSES + cls];
+    const unsigned n_children = p.child_count[depth_slot * FS_CHAINS + cls];
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
-    unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
+    unsigned* counter = &p.task_counter[depth_slot * FS_CHAINS + cls];
     for (;;) {
         unsigned long long task = 0;
         if (lane == 0) task = atomicAdd(counter, 1u);
@@ -173,7 +173,8 @@ __device__ __forceinline__ void lanes_play_unit(const SearchParams& p, LaneTable
 
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
-fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot, int half_units_per_warp)
+fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot, int half_units_per_warp,
+                        int n_warps_full)
 {
     __shared__ LaneTables<NB, W, EW> s_tb[4];
     __shared__ uint8_t s_sel8[256 * 8];
@@ -181,18 +182,20 @@ fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_
     __syncthreads();
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    const unsigned n_children = p.child_count[depth_slot * FS_CLASSES + cls];
+    const unsigned n_children = p.child_count[depth_slot * FS_CHAINS + cls];
     // Work unit = `group` consecutive 32-rollout chunks of ONE child: the problem's tables (shared
     // memory) and the child board (registers) are set up once per unit.  Units stay small
     // when there is little work (load balance) and grow up to a whole child when there is
     // plenty (>= half_units_per_warp / 2 units per resident warp; launch_rollouts_class chooses).
     const unsigned long long n_tasks = (unsigned long long)n_children * p.n_chunks;
-    const unsigned long long n_warps = (unsigned long long)gridDim.x * 4ull;
+    // (the unit size follows the warps of a FULL grid; the launch itself may hold fewer blocks when
+    // the host knows that there cannot be more units than that)
+    const unsigned long long n_warps = (unsigned long long)n_warps_full;
     const int group = (int)min((unsigned long long)p.n_chunks,
                                max(1ull, 2ull * n_tasks / (n_warps * (unsigned long long)half_units_per_warp)));
     const int groups_per_child = (p.n_chunks + group - 1) / group;
     const unsigned long long n_units = (unsigned long long)n_children * groups_per_child;
-    unsigned* counter = &p.task_counter[depth_slot * FS_CLASSES + cls];
+    unsigned* counter = &p.task_counter[depth_slot * FS_CHAINS + cls];
     int cached_key = -1;
     for (;;) {
         unsigned long long unit = 0;
@@ -619,7 +622,7 @@ __device__ __forceinline__ int advance_problem(const SearchParams& p, int prob, 
         if (status != ST_SOLVED && n_alive > 0 && r >= 0)
             atomicAdd(p.n_tiles_placed + prob, (unsigned long long)n_alive);   // one attempt per entry (:60)
         if (k > 0) {
-            base = atomicAdd(&p.child_count[next_slot * FS_CLASSES + cls], (unsigned)k);
+            base = atomicAdd(&p.child_count[next_slot * FS_CHAINS + cls], (unsigned)k);
             atomicAdd(p.rollouts_executed + prob, (unsigned long long)k * p.n_local);
         }
     }

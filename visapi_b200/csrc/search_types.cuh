@@ -18,6 +18,11 @@ constexpr int MAX_DEPTHS = BP_MAX_ENTRIES / 2 + 1;
 // (+ 4 on the plane index: boards of 65..96 columns, whose lane kernel runs with three words per
 // plane instead of four; the warp-per-board kernels of that class keep W = 4)
 constexpr int FS_CLASSES = 8 * N_CLASSES;
+// A class's problems may be dealt to several CHAINS (chain = class + FS_CLASSES * k): every chain
+// has its own child list, counters and launch sequence on its own stream, so that a small batch
+// still has enough independent launch sequences in flight to fill each other's ramps and tails.
+constexpr int FS_MAX_SUBCHAINS = 8;
+constexpr int FS_CHAINS = FS_CLASSES * FS_MAX_SUBCHAINS;
 
 enum Status : int { ST_ACTIVE = 0, ST_SOLVED = 1, ST_DEAD = 2 };
 
@@ -83,8 +88,8 @@ struct SearchParams {
     ChunkRec* rec;           // [P][ES][NC]
     ChildStats* stats;       // [P][ES]
     uint32_t* child_list;    // per class segments
-    unsigned* child_count;   // [MAX_DEPTHS + 1][FS_CLASSES]
-    unsigned* task_counter;  // [MAX_DEPTHS + 1][FS_CLASSES]
+    unsigned* child_count;   // [MAX_DEPTHS + 1][FS_CHAINS]
+    unsigned* task_counter;  // [MAX_DEPTHS + 1][FS_CHAINS]
     // lane-per-rollout tables of the current state of each problem (lanes.cuh)
     int use_lanes;
     uint32_t* planes;        // [P][8][4] bit-sliced column heights, inverted
