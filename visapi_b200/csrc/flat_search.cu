@@ -110,6 +110,11 @@ struct bp_search {
     std::vector<int> cls_list_off = std::vector<int>(FS_CHAINS, 0);    // offset into child_list
     std::vector<int> grid_rollout = std::vector<int>(FS_CHAINS, 0);
     std::vector<int> grid_lanes = std::vector<int>(FS_CHAINS, 0);
+    // launch-per-depth form on the skyline state: per chain a region of the unit ring used as a
+    // plain list, per depth and chain the number of units in it
+    std::vector<size_t> chain_unit_off = std::vector<size_t>(FS_CHAINS, 0);
+    unsigned long long* d_sky_count = nullptr;   // [MAX_DEPTHS + 1][FS_CHAINS]
+    bool sky_stepped = false;                   // the last stepped run used the skyline kernels
     int* d_cls_problems = nullptr;
     ProblemDesc* d_desc = nullptr;
     uint32_t* d_init_occ = nullptr;            // initial boards (NULL: empty boards)
@@ -328,6 +333,11 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         double upw = 4.0;
         if (const char* env = getenv("BP_RESIDENT_UPW")) upw = atof(env);
         s->x.units_per_warp_x4 = std::max(1, (int)(4.0 * upw + 0.5));
+        size_t off = 0;
+        for (int c : s->classes) {
+            s->chain_unit_off[c] = off;
+            for (int i : by_class[c]) off += (size_t)n_entries[i] * s->x.gpc_max;
+        }
     }
 
     int rc = BP_OK;
@@ -365,6 +375,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         s->counters_bytes = (size_t)(MAX_DEPTHS + 1) * FS_CHAINS * sizeof(unsigned);
         TRY(dev_alloc(s, &p.child_count, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS));
         TRY(dev_alloc(s, &p.task_counter, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS));
+        if (p.use_lanes) TRY(dev_alloc(s, &s->d_sky_count, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS));
         if (p.use_lanes) TRY(dev_alloc(s, &p.pending, P));
         if (!boards) TRY(dev_alloc(s, &p.occ, P * p.rs * p.ws));       // empty boards: zeroed too
         s->zero_end = mark();
@@ -672,6 +683,74 @@ static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t s
     s->ctx->launches++;
 }
 
+// ---- launch-per-depth form on the skyline state (search_resident.cuh) ------------------------
+// Measured (profiles/r2/shard_sweep_sky.txt): with few rollouts per child a depth is little work and
+// the advance launch between two depths is what the chain waits for -- the skyline advance takes
+// 0.67 / 2.07 ms where the warp-per-board advance takes 0.73 / 2.13 ms (125 / 1000 problems,
+// N = 100); with N = 1000 the rollouts dominate and the older pair of kernels is 1.5 % faster
+// (11.25 against 11.45 ms per set).  BP_STEPPED=sky|legacy forces one of them.
+static bool sky_stepped_ok(const bp_search* s)
+{
+    if (!(s->ring_cap != 0 && s->p.use_lanes && s->p.n_ranks == 1)) return false;
+    if (const char* env = getenv("BP_STEPPED")) {
+        if (strcmp(env, "legacy") == 0) return false;
+        if (strcmp(env, "sky") == 0) return true;
+    }
+    return s->p.n_chunks <= 8;
+}
+static int sky_upw_x4()
+{
+    static const int v = getenv("BP_SKY_UPW") ? std::max(1, (int)(4.0 * atof(getenv("BP_SKY_UPW")) + 0.5)) : 4;
+    return v;
+}
+static UnitSink sky_sink(bp_search* s, int c, int depth_slot)
+{
+    UnitSink sink;
+    sink.tail = s->d_sky_count + (size_t)depth_slot * FS_CHAINS + c;
+    sink.slots = s->x.slots + s->chain_unit_off[c];
+    sink.mask = 0xFFFFFFFFu;
+    sink.in_flight = s->cls_count[c];
+    sink.n_warps = (unsigned)s->grid_lanes[c] * 4u;
+    // (the child counters of the warp-per-board form double as the chains' active-problem counts)
+    sink.active_now = depth_slot > 0 ? s->p.child_count + (size_t)(depth_slot - 1) * FS_CHAINS + c : nullptr;
+    sink.active_next = s->p.child_count + (size_t)depth_slot * FS_CHAINS + c;
+    return sink;
+}
+static void launch_seed_sky(bp_search* s, int c, cudaStream_t st)
+{
+    const int n = s->cls_count[c];
+    ResidentParams x = s->x;
+    x.units_per_warp_x4 = sky_upw_x4();                      // half a unit per warp: whole children when there is plenty
+    fs_resident_seed_kernel<0><<<(n + ADV_WARPS - 1) / ADV_WARPS, ADV_WARPS * 32, 0, st>>>(
+        s->p, x, sky_sink(s, c, 0), s->d_cls_problems + s->cls_prob_off[c], n);
+    s->ctx->launches++;
+}
+static void launch_rollouts_sky(bp_search* s, int c, int depth, cudaStream_t st)
+{
+    const int full = s->grid_lanes[c];
+    const long long children = (long long)s->cls_count[c] * std::max(0, s->p.es - 2 * depth);
+    const long long units = std::min<long long>(children * s->p.n_chunks, children + (long long)full * 2);
+    const int grid = (int)std::max<long long>(s->ctx->sm_count, std::min<long long>(full, (units + 3) / 4));
+    const unsigned long long* list = s->x.slots + s->chain_unit_off[c];
+    const unsigned long long* count = s->d_sky_count + (size_t)depth * FS_CHAINS + c;
+    unsigned* counter = s->p.task_counter + (size_t)depth * FS_CHAINS + c;
+    dispatch_lanes(c % FS_CLASSES, [&](auto NBc, auto Wc, auto E) {
+        constexpr int NB = decltype(NBc)::value == 7 ? 8 : decltype(NBc)::value;   // the skyline playouts: 5 / 6 / 8 planes
+        fs_rollout_sky_kernel<NB, decltype(Wc)::value, decltype(E)::value>
+            <<<grid, 128, 0, st>>>(s->p, s->x, list, count, counter);
+    });
+    s->ctx->launches++;
+}
+static void launch_advance_sky(bp_search* s, int c, int depth, cudaStream_t st)
+{
+    const int n = s->cls_count[c];
+    ResidentParams x = s->x;
+    x.units_per_warp_x4 = sky_upw_x4();
+    fs_advance_sky_kernel<0><<<(n + ADV_WARPS - 1) / ADV_WARPS, ADV_WARPS * 32, 0, st>>>(
+        s->p, x, sky_sink(s, c, depth + 1), s->d_cls_problems + s->cls_prob_off[c], n);
+    s->ctx->launches++;
+}
+
 extern "C" {
 
 int bp_search_reset(bp_search* s)
@@ -859,7 +938,7 @@ int bp_search_max_depth(bp_search* s, int* max_depth)
 
 // AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt):
 // the resident kernel when a depth of the whole batch is little work -- problems x 32-rollout
-// chunks per child <= 512 (one instance at any N up to 16 384, 125 problems at N = 100) -- where
+// chunks per child <= 256 (one instance at any N up to 8 192, 64 problems at N = 100) -- where
 // the launch-per-depth form is a chain of launches with little in them; the launch-per-depth form
 // for big batches, whose playouts run ~6 % fewer instructions and share no SM with server warps.
 // A partitioned (root-parallel) search is resident: its exchange lives inside the kernel.
@@ -867,7 +946,7 @@ static int default_mode(const bp_search* s)
 {
     if (!s->ring_cap) return BP_SEARCH_STEPPED;
     if (s->p.n_ranks > 1) return BP_SEARCH_RESIDENT;
-    return (long long)s->p.n_problems * s->p.n_chunks <= 512 ? BP_SEARCH_RESIDENT : BP_SEARCH_STEPPED;
+    return (long long)s->p.n_problems * s->p.n_chunks <= 256 ? BP_SEARCH_RESIDENT : BP_SEARCH_STEPPED;
 }
 
 int bp_search_run(bp_search* s)
@@ -912,7 +991,15 @@ int bp_search_run(bp_search* s)
         if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[0], st));
         if (!s->seeded) {
             const int grid = (s->p.n_problems + ADV_WARPS - 1) / ADV_WARPS;
-            fs_resident_seed_kernel<0><<<grid, ADV_WARPS * 32, 0, st>>>(s->p, s->x, n_warps);
+            UnitSink sink;
+            sink.tail = &s->x.q->tail;
+            sink.slots = s->x.slots;
+            sink.mask = s->x.cap_mask;
+            sink.in_flight = s->x.seed_in_flight;
+            sink.n_warps = n_warps;
+            sink.active_now = nullptr;
+            sink.active_next = nullptr;
+            fs_resident_seed_kernel<0><<<grid, ADV_WARPS * 32, 0, st>>>(s->p, s->x, sink, nullptr, s->p.n_problems);
             s->ctx->launches++;
             s->seeded = true;
         }
@@ -952,11 +1039,20 @@ int bp_search_run(bp_search* s)
         BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
         for (size_t k = 0; k < s->classes.size(); ++k)
             BP_CUDA(cudaStreamWaitEvent(s->cls_stream[k], s->fork_ev, 0));
+        const bool sky = sky_stepped_ok(s);
+        s->sky_stepped = sky;
+        if (sky)
+            for (size_t k = 0; k < s->classes.size(); ++k) launch_seed_sky(s, s->classes[k], s->cls_stream[k]);
         for (int d = 0; d < s->max_depth; ++d) {
             for (size_t k = 0; k < s->classes.size(); ++k) {
                 if (d >= s->cls_depth[k]) continue;
-                launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true);
-                launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
+                if (sky) {
+                    launch_rollouts_sky(s, s->classes[k], d, s->cls_stream[k]);
+                    launch_advance_sky(s, s->classes[k], d, s->cls_stream[k]);
+                } else {
+                    launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true);
+                    launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
+                }
             }
         }
         BP_CUDA(cudaGetLastError());

@@ -174,14 +174,33 @@ __device__ __forceinline__ unsigned udiv_small(unsigned a, unsigned b)
     return q;
 }
 
+// Where the units of a problem's new depth go: the resident kernel's ring (tickets, mask =
+// capacity - 1) or, in the launch-per-depth form, the plain unit list of the problem's chain for
+// the next depth (counter = units of that launch, mask = all ones).  `in_flight` / `n_warps` size
+// the units.
+struct UnitSink {
+    unsigned long long* tail;
+    unsigned long long* slots;
+    unsigned mask;
+    int in_flight;
+    unsigned n_warps;
+    // launch-per-depth form: problems of the chain that entered the depth being advanced (read,
+    // complete when the advance launch starts) and that enter the next one (counted here)
+    const unsigned* active_now;
+    unsigned* active_next;
+};
+
 // ---- store a problem's new state and publish the units of its depth --------------------------
 // Called by a whole warp with the state in registers (the same values in every lane); the lane
 // tables and planes are already written.  `in_flight`: problems that share the machine (decides
 // the unit size: whole children while there is plenty of work, single chunks when one problem
 // has the GPU to itself).
 __device__ __forceinline__ void publish_units(const SearchParams& p, const ResidentParams& x, int prob,
-                                              ProbState& st, int in_flight, unsigned n_warps)
+                                              ProbState& st, const UnitSink& sink)
 {
+    const int in_flight = sink.active_now ? (int)*sink.active_now : sink.in_flight;
+    const unsigned n_warps = sink.n_warps;
+    if (sink.active_next && lane_id() == 0) atomicAdd(sink.active_next, 1u);
     const int lane = lane_id();
     const uint32_t lt = (1u << lane) - 1u;
     uint8_t* ul = x.ulist + (size_t)prob * p.es;
@@ -213,7 +232,7 @@ __device__ __forceinline__ void publish_units(const SearchParams& p, const Resid
     __syncwarp();
     unsigned long long t0 = 0;
     if (lane == 0) {
-        t0 = atomicAdd(&x.q->tail, (unsigned long long)n_units);
+        t0 = atomicAdd(sink.tail, (unsigned long long)n_units);
         atomicAdd(&x.q->n_units_published, (unsigned long long)n_units);
     }
     t0 = __shfl_sync(FULLMASK, t0, 0);
@@ -222,8 +241,8 @@ __device__ __forceinline__ void publish_units(const SearchParams& p, const Resid
         const uint32_t payload = (uint32_t)prob | ((uint32_t)i << RS_PROBLEM_BITS);
         const unsigned long long word =
             ((unsigned long long)payload << 32) | (unsigned long long)(uint32_t)(t + 1ull);
-        if (i < 32) st_release_u64(x.slots + (t & x.cap_mask), word);
-        else st_relaxed_u64(x.slots + (t & x.cap_mask), word);
+        if (i < 32) st_release_u64(sink.slots + (t & sink.mask), word);
+        else st_relaxed_u64(sink.slots + (t & sink.mask), word);
     }
     __syncwarp();
 }

@@ -392,6 +392,7 @@ static __device__ __noinline__ int server_replay(const uint4* gw, const uint4* g
 __device__ __forceinline__ void finish_problem(const SearchParams& p, int prob, const ProbState& st)
 {
     if (lane_id() == 0) {
+        store_state(p.pstate + prob, st);
         p.status[prob] = st.status;
         p.depth[prob] = st.depth;
         p.n_order[prob] = st.n_order;
@@ -412,7 +413,7 @@ __device__ __forceinline__ void finish_problem(const SearchParams& p, int prob, 
 // phase[] receives the cycles of (merge, commit + expand, publish).
 template <int NJ>
 __device__ __forceinline__ int server_advance_core(const SearchParams& p, const ResidentParams& x, int prob,
-                                                   unsigned n_warps, long long& c_exchange,
+                                                   UnitSink sink, long long& c_exchange,
                                                    long long (&phase)[3], uint32_t* scratch)
 {
     const int lane = lane_id();
@@ -608,8 +609,9 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
     const long long t_committed = clock64();
     if (st.status == ST_ACTIVE) {
         p.planes[(size_t)prob * LANES_PLANE_STRIDE + lane] = pw;
-        const int in_flight = __shfl_sync(FULLMASK, ld_volatile(&x.q->in_flight), 0);
-        publish_units(p, x, prob, st, in_flight, n_warps);
+        if (sink.in_flight < 0)                                  // resident: the problems still searching
+            sink.in_flight = __shfl_sync(FULLMASK, ld_volatile(&x.q->in_flight), 0);
+        publish_units(p, x, prob, st, sink);
     } else {
         finish_problem(p, prob, st);
     }
@@ -724,8 +726,9 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
             // straight line (the server SMs' instruction caches hold little more than it); more
             // children (the first moves of a large tile list) take the general form
             int status;
-            if (n_children <= 32) status = server_advance_core<1>(p, x, (int)prob, n_roll_warps, c_exch, phase, scratch);
-            else status = server_advance_core<4>(p, x, (int)prob, n_roll_warps, c_exch, phase, scratch);
+            const UnitSink sink = {&q->tail, x.slots, x.cap_mask, -1, n_roll_warps, nullptr, nullptr};
+            if (n_children <= 32) status = server_advance_core<1>(p, x, (int)prob, sink, c_exch, phase, scratch);
+            else status = server_advance_core<4>(p, x, (int)prob, sink, c_exch, phase, scratch);
             if (status != ST_ACTIVE && lane == 0) atomicSub(&q->in_flight, 1);
             c_adv += clock64() - c1;
             n_adv++;
@@ -806,13 +809,15 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
 }
 
 // ---- seed: the state record of every problem from what the reset left, depth 0 published ---
-// one warp per problem; the state arrays, legal masks and lane tables were written by the reset
+// one warp per problem (of `problems[0 .. n)`, or all of them); the state arrays, legal masks and
+// lane tables were written by the reset
 template <int UNUSED>                              // (a template so that the header owns one definition)
 __global__ void __launch_bounds__(ADV_WARPS * 32)
-fs_resident_seed_kernel(SearchParams p, ResidentParams x, unsigned n_warps)
+fs_resident_seed_kernel(SearchParams p, ResidentParams x, UnitSink sink, const int* __restrict__ problems, int n)
 {
-    const int prob = blockIdx.x * ADV_WARPS + (threadIdx.x >> 5);
-    if (prob >= p.n_problems) return;
+    const int idx = blockIdx.x * ADV_WARPS + (threadIdx.x >> 5);
+    if (idx >= n) return;
+    const int prob = problems ? problems[idx] : idx;
     if (p.status[prob] != ST_ACTIVE) return;       // solved / dead before the first move: arrays are final
     const uint4 lg = p.legal[prob], al = p.alive[prob];
     const int4 lfb = p.lfb[prob];
@@ -831,7 +836,59 @@ fs_resident_seed_kernel(SearchParams p, ResidentParams x, unsigned n_warps)
     st.pad1 = 0;
     if (st.k == 0) return;
     if (lane_id() == 0) atomicAdd(&x.q->in_flight, 1);
-    publish_units(p, x, prob, st, x.seed_in_flight, n_warps);
+    publish_units(p, x, prob, st, sink);
+}
+
+// =================================================== launch-per-depth form on the skyline state
+// The same playout and the same advance as the resident kernel, with launches as the barriers:
+// per depth and chain one rollout launch over the chain's unit list and one advance launch (one
+// warp per problem).  The tables are written once by the reset and the advance is the compact
+// skyline advance, so a depth's advance launch is a few microseconds instead of the ~19 of the
+// warp-per-board advance that rebuilt every table at every depth.
+template <int NB, int W, int EW>
+__global__ void __launch_bounds__(128)
+fs_rollout_sky_kernel(SearchParams p, ResidentParams x, const unsigned long long* __restrict__ units,
+                      const unsigned long long* __restrict__ n_units_ptr, unsigned* __restrict__ counter)
+{
+    __shared__ LaneTables<NB, W, EW> s_tb[4];
+    __shared__ uint8_t s_sel8[256 * 8];
+    fill_select_table(s_sel8);
+    __syncthreads();
+    PlayParams pp;
+    pp.desc = p.desc; pp.pstate = p.pstate; pp.planes = p.planes; pp.wmask = p.wmask; pp.hmask = p.hmask;
+    pp.pairs = reinterpret_cast<const uint4*>(p.pairs); pp.tile = p.tile; pp.ulist = x.ulist; pp.urec = x.urec;
+    pp.es = p.es; pp.n_chunks = p.n_chunks; pp.n_local = p.n_local; pp.sim_begin = p.sim_begin;
+    pp.urec_stride = x.urec_stride; pp.seed = p.seed;
+    const int lane = lane_id();
+    const int warp = threadIdx.x >> 5;
+    const unsigned long long n_units = *n_units_ptr;
+    int cached_prob = -1;
+    for (;;) {
+        unsigned unit = 0;
+        if (lane == 0) unit = atomicAdd(counter, 1u);
+        unit = __shfl_sync(FULLMASK, unit, 0);
+        if (unit >= n_units) break;
+        const uint32_t payload = (uint32_t)(units[unit] >> 32);
+        sky_play_unit<NB, W, EW>(pp, s_tb[warp], s_sel8, (int)(payload & ((1u << RS_PROBLEM_BITS) - 1u)),
+                                 (int)(payload >> RS_PROBLEM_BITS), cached_prob);
+    }
+}
+
+template <int UNUSED>
+__global__ void __launch_bounds__(ADV_WARPS * 32)
+fs_advance_sky_kernel(SearchParams p, ResidentParams x, UnitSink sink, const int* __restrict__ problems, int n)
+{
+    __shared__ __align__(16) uint32_t s_scratch[ADV_WARPS][32];
+    const int warp = threadIdx.x >> 5;
+    const int idx = blockIdx.x * ADV_WARPS + warp;
+    if (idx >= n) return;
+    const int prob = problems[idx];
+    const uint4 q1 = reinterpret_cast<const uint4*>(p.pstate + prob)[1];
+    const uint4 q4 = reinterpret_cast<const uint4*>(p.pstate + prob)[4];
+    if ((int)q4.z != ST_ACTIVE || p.status[prob] != ST_ACTIVE) return;
+    long long c_exch = 0, phase[3] = {0, 0, 0};
+    if ((int)q1.y <= 32) server_advance_core<1>(p, x, prob, sink, c_exch, phase, s_scratch[warp]);
+    else server_advance_core<4>(p, x, prob, sink, c_exch, phase, s_scratch[warp]);
 }
 
 }  // namespace bp

@@ -21,7 +21,7 @@ constexpr int FS_CLASSES = 8 * N_CLASSES;
 // A class's problems may be dealt to several CHAINS (chain = class + FS_CLASSES * k): every chain
 // has its own child list, counters and launch sequence on its own stream, so that a small batch
 // still has enough independent launch sequences in flight to fill each other's ramps and tails.
-constexpr int FS_MAX_SUBCHAINS = 8;
+constexpr int FS_MAX_SUBCHAINS = 4;
 constexpr int FS_CHAINS = FS_CLASSES * FS_MAX_SUBCHAINS;
 
 enum Status : int { ST_ACTIVE = 0, ST_SOLVED = 1, ST_DEAD = 2 };
