@@ -503,6 +503,16 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     // side streams and fork / join events come from the context's pool
     if (!ctx->fork_event) BP_CUDA(cudaEventCreateWithFlags(&ctx->fork_event, cudaEventDisableTiming));
     s->fork_ev = ctx->fork_event;
+    // heaviest chain first: stream k has priority rank k (common.cuh), so the chain whose launch
+    // sequence is the critical path gets the SM slots first and the lighter chains fill the gaps
+    {
+        auto weight = [&](int c) {
+            long long wgt = 0;
+            for (int i : by_class[c]) wgt += (long long)s->h_desc[i].rows * s->h_desc[i].cols;
+            return wgt;
+        };
+        std::stable_sort(s->classes.begin(), s->classes.end(), [&](int a, int b) { return weight(a) > weight(b); });
+    }
     for (size_t k = 0; k < s->classes.size(); ++k) {
         cudaStream_t st = side_stream(ctx, k);
         cudaEvent_t e = side_event(ctx, k);
