@@ -74,7 +74,7 @@ __global__ void probe_smid_kernel(unsigned* seen, int n)
     if (threadIdx.x == 0 && smid < (unsigned)n) seen[smid] = 1u;
     // stay a little so that the wave spreads over all SMs instead of recycling the first ones
     const long long t0 = clock64();
-    while (clock64() - t0 < 20000) {}
+    while (clock64() - t0 < 4000) {}
 }
 
 static int probe_smids(bp_context* ctx)
