@@ -499,3 +499,73 @@ def test_full_n_exact_parity_with_oracle(eng):
                 assert int(got["rollouts"][i]) == w["rollouts"]
                 assert int(got["rollout_placements"][i]) == w["rollout_placements"]
                 assert got["order"][i, :got["n_order"][i]].tolist() == w["solution_tiles_order"]
+
+
+def test_partitioned_search_error_paths(eng, golden):
+    """A partitioned search runs only in the resident form and only after its exchange buffers are
+    connected; the C ABI says so instead of hanging in a kernel that waits for peers."""
+    import visapi_b200
+    from visapi_b200 import pack_tiles
+    c = golden("flat_search.json")[0]
+    s = eng.search([c["rows"]], [c["cols"]], pack_tiles([c["tiles"]]), [len(c["tiles"])], 20, 0, 123, [0])
+    with pytest.raises(visapi_b200.EngineError, match="exchange_create"):
+        s.exchange_connect(local_ptrs=[0, 0])                  # nothing created yet
+    with pytest.raises(visapi_b200.EngineError, match="partition"):
+        s.exchange_create()                                    # not partitioned
+    s.set_partition(0, 2, 0, 10)
+    s.set_mode("resident")
+    s.reset()
+    with pytest.raises(visapi_b200.EngineError, match="exchange_connect"):
+        s.run()
+    s.set_mode("stepped")
+    s.reset()
+    with pytest.raises(visapi_b200.EngineError, match="partitioned"):
+        s.run()
+    handle, ptr = s.exchange_create()
+    assert ptr and handle.shape == (64,) and handle.any()
+    with pytest.raises(visapi_b200.EngineError, match="partition is fixed"):
+        s.set_partition(1, 2, 10, 10)
+    s.close()
+
+
+def test_root_parallel_search_object_on_one_rank(eng, golden):
+    """parallel.RootParallelSearch without a process group: both exchange forms, run twice, equal
+    the one-shot flat search."""
+    from visapi_b200 import datasets, parallel
+    probs = datasets.load_problem_set("g")[:3]
+    batch = datasets.batch_arrays(probs)
+    want = eng.flat_search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], 70, 0, 123,
+                           np.arange(3, dtype=np.uint32), want_scores=True)
+    for exchange in ("resident", "nccl"):
+        rp = parallel.RootParallelSearch(eng, batch, 70, 0, 123, np.arange(3, dtype=np.uint32), exchange=exchange)
+        for _ in range(2):
+            rp.run()
+            got = rp.results(want_scores=True)
+            for k in ("depth", "solution_found", "n_tiles_placed", "rollouts", "rollout_placements", "n_order",
+                      "order", "path", "child_scores"):
+                assert np.array_equal(got[k], want[k]), (exchange, k)
+        rp.close()
+
+
+def test_repeated_runs_replay_the_cuda_graph(eng):
+    """The launch-per-depth run of a multi-class batch is captured as a CUDA graph at its second
+    run; every run gives the same results and accounts for the same number of kernel launches."""
+    from visapi_b200 import datasets
+    probs = datasets.load_problem_set("g")[:48] + datasets.load_problem_set("b")[:16]
+    batch = datasets.batch_arrays(probs)
+    s = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], 1000, 0, 123,
+                   np.arange(len(probs), dtype=np.uint32))
+    s.set_mode("stepped")
+    assert s.info()["n_classes"] > 1
+    outs, launches = [], []
+    for _ in range(4):
+        before = eng.kernel_launches
+        s.reset()
+        s.run()
+        outs.append(s.results())
+        launches.append(eng.kernel_launches - before)
+    for o in outs[1:]:
+        for k in ("depth", "solution_found", "n_tiles_placed", "rollouts", "order"):
+            assert np.array_equal(o[k], outs[0][k])
+    assert len(set(launches)) == 1 and launches[0] > 2 * s.info()["n_classes"]
+    s.close()
