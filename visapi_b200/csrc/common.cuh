@@ -33,9 +33,6 @@ struct bp_context {
     int occ_rollout[256] = {0};
     int occ_lanes[256] = {0};
     int occ_resident[32] = {0};
-    // 0: not probed, 1: every SM id 0 .. sm_count - 1 hosts blocks (the resident search picks its
-    // server SMs by %smid), -1: it does not
-    int smid_state = 0;
 };
 
 namespace bp {

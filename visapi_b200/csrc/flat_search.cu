@@ -66,35 +66,6 @@ static void dispatch_resident(int variant, F&& f)
     }
 }
 
-// every block reports the SM it runs on (one wave of small blocks covers every SM)
-__global__ void probe_smid_kernel(unsigned* seen, int n)
-{
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-    if (threadIdx.x == 0 && smid < (unsigned)n) seen[smid] = 1u;
-    // stay a little so that the wave spreads over all SMs instead of recycling the first ones
-    const long long t0 = clock64();
-    while (clock64() - t0 < 4000) {}
-}
-
-static int probe_smids(bp_context* ctx)
-{
-    if (ctx->smid_state) return BP_OK;
-    const int n = ctx->sm_count;
-    unsigned* d_seen = nullptr;
-    BP_CUDA(cudaMalloc(&d_seen, n * sizeof(unsigned)));
-    BP_CUDA(cudaMemsetAsync(d_seen, 0, n * sizeof(unsigned), ctx->stream));
-    probe_smid_kernel<<<n * 8, 128, 0, ctx->stream>>>(d_seen, n);
-    std::vector<unsigned> seen(n);
-    BP_CUDA(cudaMemcpyAsync(seen.data(), d_seen, n * sizeof(unsigned), cudaMemcpyDeviceToHost, ctx->stream));
-    BP_CUDA(cudaStreamSynchronize(ctx->stream));
-    cudaFree(d_seen);
-    int ok = 1;
-    for (int i = 0; i < n; ++i) ok = ok && seen[i];
-    ctx->smid_state = ok ? 1 : -1;
-    return BP_OK;
-}
-
 struct bp_search {
     bp_context* ctx = nullptr;
     SearchParams p{};
@@ -482,11 +453,6 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             }
             s->grid_lanes[chain] = ctx->sm_count * ctx->occ_lanes[c];
         }
-    }
-    if (s->ring_cap) {
-        rc = probe_smids(ctx);
-        if (rc) { bp_search_destroy(s); return rc; }
-        if (ctx->smid_state < 0) s->ring_cap = 0;      // no resident search on this device
     }
     if (s->ring_cap) {
         if (!ctx->occ_resident[s->variant]) {

@@ -38,14 +38,18 @@ struct UnitQueue {
     int abort;                   // 1: a warp waited too long (watchdog), 2: unit limit exceeded
     unsigned pad_f[30];
     unsigned exited;             // warps that have left the launch
-    unsigned pad_e[31];
+    unsigned sm_order;           // SMs that have received their first block of the launch
+    unsigned pad_e[30];
+    // arrival rank (1-based) of every SM of the launch, by %smid; 0 = no block yet, ~0 = being
+    // ranked.  The SMs ranked 1 .. n_server_sms advance problems, the others play.
+    unsigned sm_rank[256];
     // where the warps' time went (SM clock cycles summed over warps, added when a warp leaves)
     unsigned long long cyc_total, cyc_wait, cyc_play, cyc_advance, cyc_exchange;
     unsigned long long n_units_played, n_advances, n_polls, n_units_published;
     unsigned long long cyc_adv_merge, cyc_adv_commit, cyc_adv_publish;   // phases of the advance
     unsigned pad_c[8];
 };
-static_assert(sizeof(UnitQueue) == 896, "queue header layout");
+static_assert(sizeof(UnitQueue) == 896 + 1024, "queue header layout");
 constexpr size_t RS_QUEUE_RESET_OFFSET = 512;     // bytes of the header a reset keeps (the ticket counters)
 
 // Kernel-parameter block of the resident search (passed by value beside SearchParams).
@@ -62,7 +66,7 @@ struct ResidentParams {
     // problems whose depth has been played, waiting for a server warp (slot = problem << 32 | ticket + 1)
     unsigned long long* done_slots;
     unsigned done_mask;
-    int n_server_sms;            // blocks on SMs 0 .. n_server_sms - 1 advance problems, the others play
+    int n_server_sms;            // the first n_server_sms SMs to receive a block advance problems, the others play
     int n_roll_warps;            // warps that play (sizes the work units)
     // root-parallel exchange over peer memory (n_ranks > 1): every rank's buffers, own included.
     // The pointers live in a small device table, not in the parameter block: indexing a parameter

@@ -291,9 +291,10 @@ static __device__ __noinline__ bool exchange_child_stats(ExchangeArgs a, int pro
 // that warp would execute ~1500 instructions of cold code under the register cap and the calling
 // convention of the playout functions, among 31 warps that keep the integer pipes busy --
 // measured 60 000 cycles per advance, on every problem's critical path.  The server warps are the
-// blocks that land on the first n_server_sms SMs (the grid is exactly one wave, every SM gets
-// its share of blocks, and a block learns its SM from %smid): those SMs run nothing else, so
-// the advance code stays in their instruction caches and issues without competition.  The
+// blocks on the first n_server_sms SMs to receive a block of the launch (elected by arrival at
+// kernel start, see the kernel; the grid is one wave, so every SM gets its share of blocks):
+// those SMs run nothing else, so the advance code stays in their instruction caches and issues
+// without competition.  The
 // code is the same for every shape class: the board is the eight bit planes of four words held ONE WORD PER
 // LANE (lane = plane * 4 + word), children are one per lane, and the width / height table rows
 // come straight from the problem's global tables.
@@ -678,8 +679,26 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
     long long phase[3] = {0, 0, 0};
     unsigned n_played = 0, n_adv = 0, n_polls = 0;
     const unsigned n_roll_warps = (unsigned)x.n_roll_warps;
-    unsigned smid;
-    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    // Role of this block: the first n_server_sms SMs that receive a block of the launch become
+    // server SMs (every block placed there advances problems), elected by arrival so that the
+    // election does not depend on how %smid is numbered or on what else runs on the device.
+    __shared__ int s_is_server;
+    if (threadIdx.x == 0) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        unsigned rank = 0xFFFFFFFEu;                           // an SM id beyond the table plays
+        if (smid < 256u) {
+            unsigned* slot = &q->sm_rank[smid];
+            if (atomicCAS(slot, 0u, 0xFFFFFFFFu) == 0u) {
+                rank = atomicAdd(&q->sm_order, 1u) + 1u;
+                st_volatile(slot, rank);
+            } else {
+                while ((rank = ld_volatile(slot)) == 0xFFFFFFFFu) __nanosleep(20);
+            }
+        }
+        s_is_server = rank <= (unsigned)x.n_server_sms ? 1 : 0;
+    }
+    __syncthreads();
 
     // take a ticket from `head_ctr` and wait for its slot in `ring`; false = the search is over
     auto take = [&](unsigned long long* head_ctr, const unsigned long long* ring, unsigned mask,
@@ -712,7 +731,7 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
         return got != 0;
     };
 
-    if (smid < (unsigned)x.n_server_sms) {
+    if (s_is_server) {
         // ---- server warps: advance the problems whose depth has been played --------------
         for (;;) {
             const long long c0 = clock64();
