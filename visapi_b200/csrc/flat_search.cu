@@ -1,6 +1,13 @@
 // Flat Monte-Carlo search (CustomMCTS.predict, binpack/MCTS.py:44-149) resident on the
-// device: many problems in flight, every depth = one rollout launch + one advance launch
-// per shape class, no host round trip until the results are read.
+// device, host side: many problems in flight, no host round trip until the results are read.
+// Two forms of one search (bp_search_run picks, results are identical):
+//   launch-per-depth   every depth = one rollout launch + one advance launch per shape class,
+//                      each class's sequence on its own stream, the whole sequence one CUDA graph
+//                      from the second run on (search_kernels.cuh; on the skyline state:
+//                      search_resident.cuh);
+//   resident           ONE launch plays every depth of every problem: unit ring, server SMs that
+//                      advance problems, in-kernel peer-memory exchange for partitioned searches
+//                      (search_resident.cuh, search_queue.cuh, resident_k*.cu).
 //
 // HBM layout (P problems, ES = entry stride, RS/WS = max rows / words per row of the batch):
 //   desc[P]            rows, cols, n_entries, class, Philox stream           (read-only)
@@ -11,6 +18,8 @@
 //   rec[P][ES][NC]     one 8-byte record per (child, chunk of 32 rollouts)
 //   stats[P][ES]       per-child statistics (root-parallel exchange buffer)
 //   child_list[]       (problem, entry) of every child of the current depth, per class
+//   pstate[P]          skyline state: one 128-byte record per problem (search_types.cuh)
+//   slots / urec / ulist / done_slots   unit ring, unit records, legal-entry lists, advance queue
 // A rollout never touches HBM except to read its root (once per 32 rollouts) and to
 // write 8 bytes per 32 rollouts; it is bound by instruction issue, not bandwidth.
 #include <algorithm>
