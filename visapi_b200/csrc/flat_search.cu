@@ -133,6 +133,8 @@ struct bp_search {
     int grid_resident = 0;
     size_t ring_cap = 0;
     UnitQueue h_queue{};                        // header as read back by bp_search_results
+    std::vector<uint8_t> h_home;                // home queue by SM arrival rank (uploaded)
+    uint8_t* d_home = nullptr;
     // root-parallel exchange over peer memory (resident search with n_ranks > 1)
     void* d_exchange = nullptr;                 // own buffer: gathered[4][R][P][ES] + arrived[P][8] + peer table
     size_t exchange_bytes = 0, exchange_flags_off = 0, exchange_table_off = 0;
@@ -300,9 +302,49 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         size_t cap = 1024;
         while (cap < sum_entries * gpc_cap && cap < (size_t(1) << 20)) cap <<= 1;
         while (cap < sum_entries) cap <<= 1;
-        s->ring_cap = cap;
-        s->x.cap_mask = (unsigned)(cap - 1);
         s->x.gpc_max = (int)std::max<size_t>(1, std::min(gpc_cap, cap / std::max<size_t>(sum_entries, 1)));
+        // One unit queue per playout class (NB planes x W words x EW entry words), heaviest first;
+        // classes beyond RS_MAX_QUEUES - 1 share the last queue.  Each queue has its own ring, sized
+        // for every unit its problems can have outstanding.
+        std::vector<long long> weight(96, 0);
+        std::vector<size_t> entries_of(96, 0);
+        auto play_class = [&](int i) {
+            const int nbi = rows[i] <= 31 ? 0 : (rows[i] <= 63 ? 1 : 2);
+            return (nbi * 4 + ((cols[i] + 31) / 32 - 1)) * 2 + (n_entries[i] <= 64 ? 0 : 1);
+        };
+        for (int i = 0; i < n_problems; ++i) {
+            const int w = (cols[i] + 31) / 32;
+            weight[play_class(i)] += (long long)rows[i] * cols[i] * (w == 1 ? 10 : (w == 2 ? 13 : (w == 3 ? 18 : 22)));
+            entries_of[play_class(i)] += (size_t)n_entries[i];
+        }
+        std::vector<int> order;
+        for (int c = 0; c < 96; ++c) if (entries_of[c]) order.push_back(c);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return weight[a] > weight[b]; });
+        std::vector<int> queue_of(96, 0);
+        s->x.n_queues = (int)std::min<size_t>(order.size(), RS_MAX_QUEUES);
+        std::vector<long long> qweight(RS_MAX_QUEUES, 0);
+        std::vector<size_t> qentries(RS_MAX_QUEUES, 0);
+        for (size_t r = 0; r < order.size(); ++r) {
+            const int k = (int)std::min<size_t>(r, RS_MAX_QUEUES - 1);
+            queue_of[order[r]] = k;
+            qweight[k] += weight[order[r]];
+            qentries[k] += entries_of[order[r]];
+        }
+        for (int i = 0; i < n_problems; ++i) s->h_desc[i].pad0 = queue_of[play_class(i)];
+        size_t ring_total = 0;
+        for (int k = 0; k < RS_MAX_QUEUES; ++k) {
+            size_t ck = 64;
+            while (ck < qentries[k] * (size_t)s->x.gpc_max) ck <<= 1;
+            s->x.ring_off[k] = (unsigned)ring_total;
+            s->x.ring_mask[k] = (unsigned)(ck - 1);
+            if (k < s->x.n_queues) ring_total += ck;
+        }
+        // (the launch-per-depth form on the skyline state uses the same memory as plain unit lists:
+        // sum_entries * gpc_max slots)
+        s->ring_cap = std::max(ring_total, sum_entries * (size_t)s->x.gpc_max);
+        // home queue of the SM with arrival rank r: the playing SMs (ranks n_server_sms + 1 ..) are
+        // dealt to the queues in proportion to their weight (area x a cost factor per plane width)
+        s->h_home.assign(256, 0);
         s->x.seed_in_flight = n_problems;
         size_t done_cap = 64;
         while (done_cap < (size_t)n_problems) done_cap <<= 1;
@@ -310,6 +352,26 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         // SMs that advance problems instead of playing (32 warps each)
         s->x.n_server_sms = n_problems >= 64 ? 2 : 1;
         if (const char* env = getenv("BP_RESIDENT_SERVERS")) s->x.n_server_sms = std::max(1, atoi(env));
+        {
+            long long total_w = 0;
+            for (int k = 0; k < s->x.n_queues; ++k) total_w += std::max<long long>(qweight[k], 1);
+            const int playing = std::max(1, ctx->sm_count - s->x.n_server_sms);
+            // arrival rank r -> the j-th playing SM -> the queue whose cumulative share covers the
+            // middle of that SM's slice
+            for (int r = 0; r < 256; ++r) {
+                const int j = ((r - s->x.n_server_sms - 1) % playing + playing) % playing;
+                const long long pos = ((2ll * j + 1) * total_w) / (2ll * playing);
+                long long acc = 0;
+                int k = 0;
+                while (k + 1 < s->x.n_queues && pos >= acc + std::max<long long>(qweight[k], 1)) {
+                    acc += std::max<long long>(qweight[k], 1);
+                    ++k;
+                }
+                s->h_home[r] = (uint8_t)k;
+            }
+            static const bool no_affinity = getenv("BP_RESIDENT_AFFINITY") && atoi(getenv("BP_RESIDENT_AFFINITY")) == 0;
+            if (no_affinity) std::fill(s->h_home.begin(), s->h_home.end(), 0);
+        }
         double upw = 4.0;
         if (const char* env = getenv("BP_RESIDENT_UPW")) upw = atof(env);
         s->x.units_per_warp_x4 = std::max(1, (int)(4.0 * upw + 0.5));
@@ -335,6 +397,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         p.desc = s->d_desc;
         TRY(dev_alloc(s, &s->d_cls_problems, cls_problems.size()));
         TRY(dev_alloc(s, &s->d_init_tiles, P * p.es * 2));
+        if (s->ring_cap) TRY(dev_alloc(s, &s->d_home, 256));
         s->up_end = mark();
         if (boards) TRY(dev_alloc(s, &s->d_init_occ, P * p.rs * p.ws));
         // queue header: its first 256 bytes (head, tail) survive a reset, the rest is zeroed with
@@ -429,6 +492,10 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
     put(s->d_desc, s->h_desc.data(), P * sizeof(ProblemDesc));
     put(s->d_cls_problems, cls_problems.data(), cls_problems.size() * sizeof(int));
     put(s->d_init_tiles, tiles, P * p.es * 2);
+    if (s->ring_cap) {
+        put(s->d_home, s->h_home.data(), 256);
+        s->x.home_tab = s->d_home;
+    }
     BP_CUDA(cudaMemcpyAsync(s->up_begin, s->h_upload.data(), s->h_upload.size(), cudaMemcpyHostToDevice,
                             ctx->stream));
     if (boards)
@@ -977,9 +1044,9 @@ int bp_search_run(bp_search* s)
         if (!s->seeded) {
             const int grid = (s->p.n_problems + ADV_WARPS - 1) / ADV_WARPS;
             UnitSink sink;
-            sink.tail = &s->x.q->tail;
-            sink.slots = s->x.slots;
-            sink.mask = s->x.cap_mask;
+            sink.tail = nullptr;                              // (per problem: the queue of its class)
+            sink.slots = nullptr;
+            sink.mask = 0;
             sink.in_flight = s->x.seed_in_flight;
             sink.n_warps = n_warps;
             sink.active_now = nullptr;

@@ -23,12 +23,23 @@ constexpr int RS_PROBLEM_BITS = 20;              // problems per resident search
 constexpr int RS_MAX_UNITS = 1 << 12;            // units of one problem's depth <= 4096
 constexpr int RS_MAX_RANKS = 8;                  // root-parallel ranks (one NVSwitch box)
 
-struct UnitQueue {
-    // every hot word on its own 128-byte line
-    unsigned long long head;     // tickets handed to consumers
+constexpr int RS_MAX_QUEUES = 8;     // unit queues of a search: one per shape class (the last one shared)
+
+// one unit queue: tickets handed to consumers / reserved by producers, each on its own line
+struct ClassQueue {
+    unsigned long long head;
     unsigned pad_h[30];
-    unsigned long long tail;     // tickets reserved by producers
+    unsigned long long tail;
     unsigned pad_t[30];
+};
+
+struct UnitQueue {
+    // every hot word on its own 128-byte line.  One unit queue per shape class: an SM has a HOME
+    // class and takes its units from that queue while there are any, so that its instruction caches
+    // hold one class's playout instead of all of them (four mixed playouts cost the resident
+    // kernel 16 % -- `no_instruction` was its top stall -- against 4.6 % with one class); a warp
+    // that finds its home queue empty takes from the next one.
+    ClassQueue cq[RS_MAX_QUEUES];
     unsigned long long done_head;   // the same pair for the queue of problems waiting for their advance
     unsigned pad_dh[30];
     unsigned long long done_tail;
@@ -49,14 +60,17 @@ struct UnitQueue {
     unsigned long long cyc_adv_merge, cyc_adv_commit, cyc_adv_publish;   // phases of the advance
     unsigned pad_c[8];
 };
-static_assert(sizeof(UnitQueue) == 896 + 1024, "queue header layout");
-constexpr size_t RS_QUEUE_RESET_OFFSET = 512;     // bytes of the header a reset keeps (the ticket counters)
+static_assert(sizeof(UnitQueue) == 256 * RS_MAX_QUEUES + 256 + 384 + 1024, "queue header layout");
+constexpr size_t RS_QUEUE_RESET_OFFSET = 256 * RS_MAX_QUEUES + 256;   // bytes of the header a reset keeps (the ticket counters)
 
 // Kernel-parameter block of the resident search (passed by value beside SearchParams).
 struct ResidentParams {
     UnitQueue* q;
-    unsigned long long* slots;
-    unsigned cap_mask;           // ring capacity - 1
+    unsigned long long* slots;   // the rings of all unit queues (and, launch-per-depth, the chains' unit lists)
+    int n_queues;
+    unsigned ring_off[RS_MAX_QUEUES];    // first slot of queue k's ring
+    unsigned ring_mask[RS_MAX_QUEUES];   // its capacity - 1
+    const uint8_t* home_tab;     // [256] home queue of the SM with arrival rank r
     int gpc_max;                 // most units one child may be split into
     int units_per_warp_x4;       // target units in flight per resident warp, times 4
     int seed_in_flight;          // problems assumed in flight while depth 0 is being published

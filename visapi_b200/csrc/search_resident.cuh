@@ -682,8 +682,12 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
     // Role of this block: the first n_server_sms SMs that receive a block of the launch become
     // server SMs (every block placed there advances problems), elected by arrival so that the
     // election does not depend on how %smid is numbered or on what else runs on the device.
-    __shared__ int s_is_server;
+    __shared__ int s_is_server, s_home;
+    __shared__ unsigned s_ring_off[RS_MAX_QUEUES], s_ring_mask[RS_MAX_QUEUES];
     if (threadIdx.x == 0) {
+        // (constant indices: a run-time index into the parameter block would move it to local memory)
+#pragma unroll
+        for (int k = 0; k < RS_MAX_QUEUES; ++k) { s_ring_off[k] = x.ring_off[k]; s_ring_mask[k] = x.ring_mask[k]; }
         unsigned smid;
         asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
         unsigned rank = 0xFFFFFFFEu;                           // an SM id beyond the table plays
@@ -697,8 +701,10 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
             }
         }
         s_is_server = rank <= (unsigned)x.n_server_sms ? 1 : 0;
+        s_home = rank < 256u ? (int)x.home_tab[rank] : 0;       // the playout this SM keeps in its caches
     }
     __syncthreads();
+    const int home = s_home, n_queues = x.n_queues;
 
     // take a ticket from `head_ctr` and wait for its slot in `ring`; false = the search is over
     auto take = [&](unsigned long long* head_ctr, const unsigned long long* ring, unsigned mask,
@@ -731,6 +737,61 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
         return got != 0;
     };
 
+    // rollout warps: a unit from the home queue while it has any, else from the next queue that
+    // has; a warp only takes a ticket where it has just seen head < tail (a lost race leaves it
+    // with a ticket for the next unit published there, which it waits for)
+    auto take_unit = [&](uint32_t& payload) -> bool {
+        int got = 0;
+        payload = 0;
+        if (lane == 0) {
+            unsigned ns = 32;
+            unsigned long long t_begin = 0;
+            for (;;) {
+                int k = -1;
+                if (n_queues == 1) {
+                    k = 0;
+                } else {
+                    for (int i = 0; i < n_queues; ++i) {
+                        const int c = home + i < n_queues ? home + i : home + i - n_queues;
+                        if (ld_relaxed_u64(&q->cq[c].tail) > ld_relaxed_u64(&q->cq[c].head)) { k = c; break; }
+                    }
+                }
+                if (k >= 0) {
+                    const unsigned long long ticket = atomicAdd(&q->cq[k].head, 1ull);
+                    const unsigned long long* sl = x.slots + s_ring_off[k] + (ticket & s_ring_mask[k]);
+                    const uint32_t want = (uint32_t)(ticket + 1ull);
+                    for (;;) {
+                        const unsigned long long v = ld_relaxed_u64(sl);
+                        if ((uint32_t)v == want) { payload = (uint32_t)(v >> 32); got = 1; break; }
+                        if (ld_volatile(&q->in_flight) <= 0 || ld_volatile(&q->abort)) break;
+                        ++n_polls;
+                        __nanosleep(ns);
+                        if (ns < 256) ns *= 2;
+                        else {
+                            const unsigned long long now = global_timer_ns();
+                            if (t_begin == 0) t_begin = now;
+                            else if (now - t_begin > 4000000000ull) { st_volatile(&q->abort, 1); break; }
+                        }
+                    }
+                    break;
+                }
+                if (ld_volatile(&q->in_flight) <= 0 || ld_volatile(&q->abort)) break;
+                ++n_polls;
+                __nanosleep(ns);
+                if (ns < 256) ns *= 2;
+                else {
+                    const unsigned long long now = global_timer_ns();
+                    if (t_begin == 0) t_begin = now;
+                    else if (now - t_begin > 4000000000ull) { st_volatile(&q->abort, 1); break; }
+                }
+            }
+        }
+        got = __shfl_sync(FULLMASK, got, 0);
+        payload = __shfl_sync(FULLMASK, payload, 0);
+        __syncwarp();
+        return got != 0;
+    };
+
     if (s_is_server) {
         // ---- server warps: advance the problems whose depth has been played --------------
         for (;;) {
@@ -745,7 +806,9 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
             // straight line (the server SMs' instruction caches hold little more than it); more
             // children (the first moves of a large tile list) take the general form
             int status;
-            const UnitSink sink = {&q->tail, x.slots, x.cap_mask, -1, n_roll_warps, nullptr, nullptr};
+            const int qk = p.desc[prob].pad0;                   // the unit queue of the problem's class
+            const UnitSink sink = {&q->cq[qk].tail, x.slots + s_ring_off[qk], s_ring_mask[qk], -1,
+                                   n_roll_warps, nullptr, nullptr};
             if (n_children <= 32) status = server_advance_core<1>(p, x, (int)prob, sink, c_exch, phase, scratch);
             else status = server_advance_core<4>(p, x, (int)prob, sink, c_exch, phase, scratch);
             if (status != ST_ACTIVE && lane == 0) atomicSub(&q->in_flight, 1);
@@ -758,7 +821,7 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
         for (;;) {
             const long long c0 = clock64();
             uint32_t payload;
-            if (!take(&q->head, x.slots, x.cap_mask, payload)) break;
+            if (!take_unit(payload)) break;
             const int prob = (int)(payload & ((1u << RS_PROBLEM_BITS) - 1u));
             const int uidx = (int)(payload >> RS_PROBLEM_BITS);
             const ProblemDesc d = p.desc[prob];
@@ -815,10 +878,12 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
         // the last warp out leaves empty queues behind: tickets handed out but never served
         // are forgotten, the next launch publishes from `head` on
         if (atomicAdd(&q->exited, 1u) == gridDim.x * 4u - 1u) {
-            const unsigned long long h = ld_volatile(&q->head), t = ld_volatile(&q->tail);
-            const unsigned long long m = h > t ? h : t;
-            st_volatile(&q->head, m);
-            st_volatile(&q->tail, m);
+            for (int k = 0; k < RS_MAX_QUEUES; ++k) {
+                const unsigned long long h = ld_volatile(&q->cq[k].head), t = ld_volatile(&q->cq[k].tail);
+                const unsigned long long m = h > t ? h : t;
+                st_volatile(&q->cq[k].head, m);
+                st_volatile(&q->cq[k].tail, m);
+            }
             const unsigned long long dh = ld_volatile(&q->done_head), dt = ld_volatile(&q->done_tail);
             const unsigned long long dm = dh > dt ? dh : dt;
             st_volatile(&q->done_head, dm);
@@ -855,6 +920,12 @@ fs_resident_seed_kernel(SearchParams p, ResidentParams x, UnitSink sink, const i
     st.pad1 = 0;
     if (st.k == 0) return;
     if (lane_id() == 0) atomicAdd(&x.q->in_flight, 1);
+    if (sink.slots == nullptr) {                   // resident search: the unit queue of the problem's class
+        const int qk = p.desc[prob].pad0;
+        sink.tail = &x.q->cq[qk].tail;
+        sink.slots = x.slots + x.ring_off[qk];
+        sink.mask = x.ring_mask[qk];
+    }
     publish_units(p, x, prob, st, sink);
 }
 
