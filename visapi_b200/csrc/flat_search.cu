@@ -988,17 +988,19 @@ int bp_search_max_depth(bp_search* s, int* max_depth)
     return BP_OK;
 }
 
-// AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt):
-// the resident kernel when a depth of the whole batch is little work -- problems x 32-rollout
-// chunks per child <= 256 (one instance at any N up to 8 192, 64 problems at N = 100) -- where
-// the launch-per-depth form is a chain of launches with little in them; the launch-per-depth form
-// for big batches, whose playouts run ~6 % fewer instructions and share no SM with server warps.
-// A partitioned (root-parallel) search is resident: its exchange lives inside the kernel.
+// AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt, root_parallel_*.json,
+// DESIGN.md section 4).  With the grid bound, the CUDA graph and the skyline advance kernel the
+// launch-per-depth form wins every batch of 20-tile problems from 1 to 1000 at N = 100 and 1000
+// (0.27 / 0.31 ms for one instance, 1.97 / 2.10 ms for 125, 11.2 / 12.3 ms for 1000), because its
+// per-class kernels run ~6 % fewer instructions and give no SM to server warps.  The resident
+// kernel wins where a search is a long chain of moves with little work each: one large instance
+// (50 tiles: 4.90 / 5.23 ms at N = 5000, 45.7 / 73.1 ms at N = 100 000), and it is the only form that
+// runs a partitioned (root-parallel) search without a host step per move.
 static int default_mode(const bp_search* s)
 {
     if (!s->ring_cap) return BP_SEARCH_STEPPED;
     if (s->p.n_ranks > 1) return BP_SEARCH_RESIDENT;
-    return (long long)s->p.n_problems * s->p.n_chunks <= 256 ? BP_SEARCH_RESIDENT : BP_SEARCH_STEPPED;
+    return (s->p.n_problems <= 4 && s->max_depth > 32) ? BP_SEARCH_RESIDENT : BP_SEARCH_STEPPED;
 }
 
 int bp_search_run(bp_search* s)
