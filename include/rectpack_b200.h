@@ -160,9 +160,16 @@ int bp_search_reset(bp_search *s);
  *                       advance independently.  Needs the lane kernel (see bp_search_info) and
  *                       fewer than 2^20 problems; the only form that runs a partitioned
  *                       (root-parallel) search without a host step per move;
- *   BP_SEARCH_AUTO      the faster of the two as measured on B200.
- * The environment variable BP_SEARCH=stepped|resident overrides the mode. */
-typedef enum { BP_SEARCH_AUTO = 0, BP_SEARCH_STEPPED = 1, BP_SEARCH_RESIDENT = 2 } bp_search_mode;
+ *   BP_SEARCH_HYBRID    the first depths (plenty of work each) launch-per-depth, the remaining
+ *                       ones -- where a launch-per-depth step is mostly launch gaps and kernel
+ *                       tails -- by the resident kernel: every chain's last advance hands its live
+ *                       problems to the resident kernel's queues.  Same requirements as
+ *                       BP_SEARCH_RESIDENT, single rank only; falls back to one of the two pure
+ *                       forms when the hand-over depth is the first or the last one;
+ *   BP_SEARCH_AUTO      the fastest of these as measured on B200.
+ * The environment variable BP_SEARCH=stepped|resident|hybrid overrides the mode.
+ * bp_search_last_run: 0 = launch-per-depth, 1 = resident, 2 = hybrid. */
+typedef enum { BP_SEARCH_AUTO = 0, BP_SEARCH_STEPPED = 1, BP_SEARCH_RESIDENT = 2, BP_SEARCH_HYBRID = 3 } bp_search_mode;
 int bp_search_set_mode(bp_search *s, int mode);
 /* on != 0: time the launches of the next run with CUDA events on the context's stream, shape
  * classes serialised.  bp_search_profile synchronises and returns, for the last run,

@@ -374,22 +374,27 @@ def test_search_reset_is_repeatable(eng, golden):
 
 
 @pytest.mark.parametrize("set_name,strategy,n_sim", [("g", 0, 100), ("b", 1, 37), ("g", 1, 1000)])
-def test_resident_search_equals_stepped(eng, set_name, strategy, n_sim):
+def test_resident_search_equals_stepped(eng, monkeypatch, set_name, strategy, n_sim):
     """The single-launch resident search (problems advance independently, the warp that finishes
-    a depth commits it) returns exactly what the launch-per-depth search returns: every field,
-    every child score, for a mixed-class batch."""
+    a depth commits it) and the hybrid form (launch-per-depth, then resident) return exactly what
+    the launch-per-depth search returns: every field, every child score, for a mixed-class batch."""
     from visapi_b200 import datasets
     probs = datasets.load_problem_set(set_name)[:300]
     batch = datasets.batch_arrays(probs)
     s = eng.search(batch["rows"], batch["cols"], batch["tiles"], batch["n_entries"], n_sim, strategy, 123)
     assert s.info()["lane_kernel"]
     ref = None
-    for mode in ("stepped", "resident", "resident"):
+    # (hybrid: 6 depths launch-per-depth, then the resident kernel; twice, the second run from the
+    # captured graph, and once with the hand-over after the first depth)
+    for mode, handover in (("stepped", None), ("resident", None), ("resident", None), ("hybrid", 6),
+                           ("hybrid", 6), ("hybrid", 1), ("hybrid", 6)):
+        if handover is not None:
+            monkeypatch.setenv("BP_HYBRID_DEPTH", str(handover))
         s.set_mode(mode)
         s.reset()
         s.run()
         res = s.results(want_scores=True)
-        assert s.last_run_resident() == (mode == "resident")
+        assert s.last_run_form() == mode
         if ref is None:
             ref = res
         for k in ("depth", "solution_found", "score", "n_order", "n_tiles_placed", "rollouts",

@@ -47,7 +47,7 @@ def child(a):
            "placements_executed": int(res["placements_executed"].sum()),
            "digest": int(np.bitwise_xor.reduce(res["rollouts"].astype(np.uint64) * np.uint64(2654435761)
                                                + res["depth"].astype(np.uint64)))}
-    if s.last_run_resident():
+    if s.last_run_form() != "stepped":
         out["resident"] = {k: (round(v, 4) if isinstance(v, float) else v) for k, v in s.resident_stats().items()}
         out["resident"]["advance_cycles"] = {k: int(v) for k, v in out["resident"]["advance_cycles"].items()}
     if a.dump:

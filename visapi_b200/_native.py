@@ -411,15 +411,20 @@ class Search(object):
         self.engine._check(self._lib.bp_search_run(self._h))
 
     def set_mode(self, mode):
-        """"stepped" (one launch pair per depth and class), "resident" (one launch per class runs
-        every depth) or "auto" (the faster one as measured: stepped)."""
+        """"stepped" (one launch pair per depth and class), "resident" (one launch runs every
+        depth), "hybrid" (launch-per-depth while a depth is plenty of work, then the resident
+        kernel) or "auto" (the fastest one as measured)."""
         self.engine._check(self._lib.bp_search_set_mode(
-            self._h, {"auto": 0, "stepped": 1, "resident": 2}[mode]))
+            self._h, {"auto": 0, "stepped": 1, "resident": 2, "hybrid": 3}[mode]))
 
-    def last_run_resident(self):
+    def last_run_form(self):
+        """"stepped" | "resident" | "hybrid": how the last bp_search_run played the search."""
         r = C.c_int()
         self.engine._check(self._lib.bp_search_last_run(self._h, C.byref(r)))
-        return bool(r.value)
+        return ("stepped", "resident", "hybrid")[r.value]
+
+    def last_run_resident(self):
+        return self.last_run_form() == "resident"
 
     def resident_stats(self):
         """Time split of the warps of the last resident run (see bp_search_resident_stats)."""

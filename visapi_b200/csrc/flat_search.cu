@@ -106,6 +106,9 @@ struct bp_search {
     char *res_end = nullptr, *ff_begin = nullptr, *ff_end = nullptr;
     std::vector<char> h_upload, h_results;      // host images of the upload / result block
     bool in_profiled_run = false;               // bp_search_run is stepping the depths itself
+#ifdef BP_TIMELINE
+    unsigned long long* d_timeline = nullptr;   // debug build: per-launch warp time stamps
+#endif
     bool arena_from_ctx = false;
     size_t counters_bytes = 0;
     // optional per-depth CUDA-event timing of the rollout and advance launches
@@ -122,6 +125,7 @@ struct bp_search {
     // graph launch replaces ~2 x depths x chains kernel launches and their stream fork / join
     cudaGraphExec_t graph_exec = nullptr;
     int graph_launches = 0;                     // kernel nodes in the graph
+    int graph_key = 0;                          // which form the graph holds (0: launch-per-depth, 1 + K: hybrid)
     int n_runs = 0;
     // resident search (one launch runs every depth of every problem): queue, ring, variant
     int mode = BP_SEARCH_AUTO;
@@ -132,6 +136,8 @@ struct bp_search {
     int variant = 0;
     int grid_resident = 0;
     size_t ring_cap = 0;
+    size_t list_base = 0;                       // first slot of the launch-per-depth unit lists
+    int hybrid_depths = 0;                      // depths the last hybrid run played launch-per-depth
     UnitQueue h_queue{};                        // header as read back by bp_search_results
     std::vector<uint8_t> h_home;                // home queue by SM arrival rank (uploaded)
     uint8_t* d_home = nullptr;
@@ -339,9 +345,11 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             s->x.ring_mask[k] = (unsigned)(ck - 1);
             if (k < s->x.n_queues) ring_total += ck;
         }
-        // (the launch-per-depth form on the skyline state uses the same memory as plain unit lists:
-        // sum_entries * gpc_max slots)
-        s->ring_cap = std::max(ring_total, sum_entries * (size_t)s->x.gpc_max);
+        // (the launch-per-depth form on the skyline state keeps its chains' unit lists behind the
+        // rings: sum_entries * gpc_max slots.  Separate memory, because the hybrid form plays the first
+        // depths from the lists and hands over to the resident kernel chain by chain.)
+        s->ring_cap = ring_total + sum_entries * (size_t)s->x.gpc_max;
+        s->list_base = ring_total;
         // home queue of the SM with arrival rank r: the playing SMs (ranks n_server_sms + 1 ..) are
         // dealt to the queues in proportion to their weight (area x a cost factor per plane width)
         s->h_home.assign(256, 0);
@@ -375,7 +383,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
         double upw = 4.0;
         if (const char* env = getenv("BP_RESIDENT_UPW")) upw = atof(env);
         s->x.units_per_warp_x4 = std::max(1, (int)(4.0 * upw + 0.5));
-        size_t off = 0;
+        size_t off = s->list_base;
         for (int c : s->classes) {
             s->chain_unit_off[c] = off;
             for (int i : by_class[c]) off += (size_t)n_entries[i] * s->x.gpc_max;
@@ -677,17 +685,37 @@ int bp_search_set_resident_blocks(bp_search* s, int blocks_per_sm)
 
 }  // extern "C"
 
+// Kernel launch, optionally as a programmatic dependent launch: the kernel may start while the
+// kernel before it in the stream is still running and waits for it in grid_dependency_wait().
+// A chain's launches are rollouts(d) -> advance(d) -> rollouts(d + 1) ...; on the device timeline
+// (tools/timeline.py) the 4-8 us between the end of one and the first warp of the next were a
+// quarter of a late depth's ~45 us.
+template <typename... KArgs, typename... Args>
+static void launch_kernel(void (*kernel)(KArgs...), int grid, int block, cudaStream_t st, bool pdl, Args... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid);
+    cfg.blockDim = dim3((unsigned)block);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr;
+    attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr.val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = pdl ? 1 : 0;
+    cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 template <bool FIRST>
 static void launch_advance_class(bp_search* s, int c, int next_slot, const ChildStats* gathered,
-                                 cudaStream_t st)
+                                 cudaStream_t st, bool pdl = false)
 {
     const int n = s->cls_count[c];
     const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
     dispatch_class((c % FS_CLASSES) % N_CLASSES, [&](auto R, auto Wc, auto E) {
-        fs_advance_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value, FIRST>
-            <<<grid, ADV_WARPS * 32, 0, st>>>(s->p, c, s->cls_list_off[c],
-                                              s->d_cls_problems + s->cls_prob_off[c], n, next_slot,
-                                              gathered);
+        launch_kernel(fs_advance_kernel<decltype(R)::value, decltype(Wc)::value, decltype(E)::value, FIRST>,
+                      grid, ADV_WARPS * 32, st, pdl, s->p, c, s->cls_list_off[c],
+                      (const int*)(s->d_cls_problems + s->cls_prob_off[c]), n, next_slot, gathered);
     });
     s->ctx->launches++;
 }
@@ -706,7 +734,8 @@ static void launch_advance(bp_search* s, int next_slot, const ChildStats* gather
 // sum of the rollout kernels is 13.52 / 13.53 / 14.04 / 14.88 ms, so it keeps small units.
 // Half a unit per warp (whole children almost always) gives another 2 % (4 % at N = 100); smaller
 // values change nothing, the unit is capped at one child.
-static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t st, bool overlapped)
+static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t st, bool overlapped,
+                                  bool pdl = false)
 {
     int upw = overlapped ? 1 : 16;                            // in half units: 0.5 / 8 units per warp
     if (const char* env = getenv("BP_UNITS_PER_WARP")) upw = std::max(1, (int)(2.0 * atof(env) + 0.5));
@@ -723,8 +752,8 @@ static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t s
         const int grid = shrink ? (int)std::max<long long>(s->ctx->sm_count, std::min<long long>(full, (units + 3) / 4))
                                 : full;
         dispatch_lanes(c % FS_CLASSES, [&](auto NBc, auto Wc, auto E) {
-            fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>
-                <<<grid, 128, 0, st>>>(s->p, c, s->cls_list_off[c], depth, upw, full * 4);
+            launch_kernel(fs_rollout_lanes_kernel<decltype(NBc)::value, decltype(Wc)::value, decltype(E)::value>,
+                          grid, 128, st, pdl, s->p, c, s->cls_list_off[c], depth, upw, full * 4);
         });
     }
     else
@@ -777,7 +806,7 @@ static void launch_seed_sky(bp_search* s, int c, cudaStream_t st)
         s->p, x, sky_sink(s, c, 0), s->d_cls_problems + s->cls_prob_off[c], n);
     s->ctx->launches++;
 }
-static void launch_rollouts_sky(bp_search* s, int c, int depth, cudaStream_t st)
+static void launch_rollouts_sky(bp_search* s, int c, int depth, cudaStream_t st, bool pdl = false)
 {
     const int full = s->grid_lanes[c];
     const long long children = (long long)s->cls_count[c] * std::max(0, s->p.es - 2 * depth);
@@ -788,19 +817,50 @@ static void launch_rollouts_sky(bp_search* s, int c, int depth, cudaStream_t st)
     unsigned* counter = s->p.task_counter + (size_t)depth * FS_CHAINS + c;
     dispatch_lanes(c % FS_CLASSES, [&](auto NBc, auto Wc, auto E) {
         constexpr int NB = decltype(NBc)::value == 7 ? 8 : decltype(NBc)::value;   // the skyline playouts: 5 / 6 / 8 planes
-        fs_rollout_sky_kernel<NB, decltype(Wc)::value, decltype(E)::value>
-            <<<grid, 128, 0, st>>>(s->p, s->x, list, count, counter);
+        launch_kernel(fs_rollout_sky_kernel<NB, decltype(Wc)::value, decltype(E)::value>, grid, 128, st, pdl,
+                      s->p, s->x, list, count, counter);
     });
     s->ctx->launches++;
 }
-static void launch_advance_sky(bp_search* s, int c, int depth, cudaStream_t st)
+static void launch_advance_sky(bp_search* s, int c, int depth, cudaStream_t st, bool handover = false,
+                               bool pdl = false)
 {
     const int n = s->cls_count[c];
-    ResidentParams x = s->x;
-    x.units_per_warp_x4 = sky_upw_x4();
-    fs_advance_sky_kernel<0><<<(n + ADV_WARPS - 1) / ADV_WARPS, ADV_WARPS * 32, 0, st>>>(
-        s->p, x, sky_sink(s, c, depth + 1), s->d_cls_problems + s->cls_prob_off[c], n);
+    const int grid = (n + ADV_WARPS - 1) / ADV_WARPS;
+    const int* problems = s->d_cls_problems + s->cls_prob_off[c];
+    if (handover) {
+        // the chain's last launch-per-depth advance: units of the next depth go to the resident
+        // kernel's queues, sized for its warps
+        UnitSink sink = sky_sink(s, c, depth + 1);
+        sink.n_warps = (unsigned)s->x.n_roll_warps;
+        launch_kernel(fs_advance_sky_kernel<1>, grid, ADV_WARPS * 32, st, pdl, s->p, s->x, sink, problems, n,
+                      s->p.n_problems);
+    } else {
+        ResidentParams x = s->x;
+        x.units_per_warp_x4 = sky_upw_x4();
+        launch_kernel(fs_advance_sky_kernel<0>, grid, ADV_WARPS * 32, st, pdl, s->p, x, sky_sink(s, c, depth + 1),
+                      problems, n, s->p.n_problems);
+    }
     s->ctx->launches++;
+}
+
+// Hybrid form: the depths with plenty of work are played launch-per-depth (per-class kernels, no
+// SM given to server warps), the rest by the resident kernel.  The device timeline of the
+// launch-per-depth form (tools/timeline.py, profiles/r2/timeline_*.txt) shows why: once a depth is a
+// few tens of microseconds of work, each one costs ~45 us -- rollout ramp and tail, two launch
+// gaps of 4-8 us, an advance launch of ~15 us -- and every chain pays it for every remaining depth
+// (the last 13 depths of a 125-problem shard are 600 us of its 2.1 ms with the GPU a third full).
+// In the resident kernel a problem's next depth starts as soon as its own units are done.
+// Work of depth d ~ 2 P N (D - d)^2 placements (P problems, N rollouts per child, D tiles); the
+// hand-over is at the first depth whose work is below BP_HYBRID_WORK (default 5e7).
+static int hybrid_handover_depth(const bp_search* s)
+{
+    if (const char* env = getenv("BP_HYBRID_DEPTH")) return std::max(0, std::min(atoi(env), s->max_depth));
+    double work = 5e7;
+    if (const char* env = getenv("BP_HYBRID_WORK")) work = atof(env);
+    const double per = 2.0 * (double)s->p.n_problems * (double)s->p.n_sim;
+    const int rest = (int)std::floor(std::sqrt(work / per));
+    return std::max(0, std::min(s->max_depth - rest, s->max_depth));
 }
 
 extern "C" {
@@ -852,7 +912,8 @@ int bp_search_set_profiling(bp_search* s, int on)
 int bp_search_set_mode(bp_search* s, int mode)
 {
     BP_REQUIRE(s != nullptr, "search is null");
-    BP_REQUIRE(mode == BP_SEARCH_AUTO || mode == BP_SEARCH_STEPPED || mode == BP_SEARCH_RESIDENT, "mode");
+    BP_REQUIRE(mode == BP_SEARCH_AUTO || mode == BP_SEARCH_STEPPED || mode == BP_SEARCH_RESIDENT ||
+               mode == BP_SEARCH_HYBRID, "mode");
     s->mode = mode;
     return BP_OK;
 }
@@ -951,7 +1012,7 @@ int bp_search_info(bp_search* s, int* lane_kernel, int* n_classes)
 int bp_search_last_run(bp_search* s, int* resident)
 {
     BP_REQUIRE(s && resident, "null argument");
-    *resident = s->ran_resident ? 1 : 0;
+    *resident = s->ran_resident ? (s->hybrid_depths > 0 ? 2 : 1) : 0;
     return BP_OK;
 }
 
@@ -1010,8 +1071,21 @@ int bp_search_run(bp_search* s)
     if (const char* env = getenv("BP_SEARCH")) {
         if (strcmp(env, "resident") == 0) mode = BP_SEARCH_RESIDENT;
         else if (strcmp(env, "stepped") == 0) mode = BP_SEARCH_STEPPED;
+        else if (strcmp(env, "hybrid") == 0) mode = BP_SEARCH_HYBRID;
     }
     if (mode == BP_SEARCH_AUTO) mode = default_mode(s);
+    int handover = -1;                           // hybrid: depths played launch-per-depth
+    if (mode == BP_SEARCH_HYBRID) {
+        if (!s->ring_cap || s->p.n_ranks != 1) {
+            set_error("the hybrid search needs the lane kernel (empty initial boards, equal tiles adjacent "
+                      "in every list) and an unpartitioned search");
+            return BP_ERR_STATE;
+        }
+        handover = hybrid_handover_depth(s);
+        if (handover <= 0) mode = BP_SEARCH_RESIDENT;
+        else if (handover >= s->max_depth - 1) mode = BP_SEARCH_STEPPED;
+    }
+    s->hybrid_depths = mode == BP_SEARCH_HYBRID ? handover : 0;
     if (s->p.n_ranks != 1 && mode != BP_SEARCH_RESIDENT) {
         set_error("bp_search_run of a partitioned search needs the resident kernel (or use the "
                   "step API with an all-gather per move)");
@@ -1042,6 +1116,7 @@ int bp_search_run(bp_search* s)
         }
         s->x.n_roll_warps = (s->ctx->sm_count - s->x.n_server_sms) * blocks_per_sm * 4;
         const unsigned n_warps = (unsigned)s->x.n_roll_warps;
+        s->hybrid_depths = 0;
         if (s->profiling) BP_CUDA(cudaEventRecord(s->ev[0], st));
         if (!s->seeded) {
             const int grid = (s->p.n_problems + ADV_WARPS - 1) / ADV_WARPS;
@@ -1071,7 +1146,8 @@ int bp_search_run(bp_search* s)
         s->cur_depth = s->max_depth;
         return BP_OK;
     }
-    if (s->profiling || s->classes.size() == 1 || getenv("BP_SERIAL_CLASSES")) {
+    const bool hybrid = mode == BP_SEARCH_HYBRID;
+    if (!hybrid && (s->profiling || s->classes.size() == 1 || getenv("BP_SERIAL_CLASSES"))) {
         s->in_profiled_run = s->profiling;
         int rc = BP_OK;
         while (!rc && s->cur_depth < s->max_depth) {
@@ -1085,27 +1161,43 @@ int bp_search_run(bp_search* s)
         set_error("bp_search_run: call bp_search_reset first");
         return BP_ERR_STATE;
     }
+    if (hybrid) {
+        if (s->x.n_server_sms >= s->ctx->sm_count) {
+            set_error("resident search: %d server SMs leave nothing to play on", s->x.n_server_sms);
+            return BP_ERR_STATE;
+        }
+        s->x.n_roll_warps = (s->ctx->sm_count - s->x.n_server_sms) * (s->grid_resident / s->ctx->sm_count) * 4;
+    }
     // fork: every chain runs its whole depth loop on its own stream, then join.  Launches are
     // issued depth-major (all chains' depth 0, then depth 1, ...) so that every chain starts
     // at once instead of waiting for the host to issue the chains before it.
     BP_CUDA(cudaSetDevice(s->ctx->device));
+    static const bool pdl = !(getenv("BP_PDL") && atoi(getenv("BP_PDL")) == 0);
     auto issue = [&]() -> int {
+#ifdef BP_TIMELINE
+        if (!s->d_timeline) {
+            BP_CUDA(cudaMalloc(&s->d_timeline, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS * 2 * 4 * 8));
+            BP_CUDA(cudaMemcpyToSymbol(g_timeline, &s->d_timeline, sizeof(s->d_timeline)));
+        }
+        BP_CUDA(cudaMemsetAsync(s->d_timeline, 0, (size_t)(MAX_DEPTHS + 1) * FS_CHAINS * 2 * 4 * 8, s->ctx->stream));
+#endif
         BP_CUDA(cudaEventRecord(s->fork_ev, s->ctx->stream));
         for (size_t k = 0; k < s->classes.size(); ++k)
             BP_CUDA(cudaStreamWaitEvent(s->cls_stream[k], s->fork_ev, 0));
-        const bool sky = sky_stepped_ok(s);
+        const bool sky = hybrid || sky_stepped_ok(s);
         s->sky_stepped = sky;
         if (sky)
             for (size_t k = 0; k < s->classes.size(); ++k) launch_seed_sky(s, s->classes[k], s->cls_stream[k]);
-        for (int d = 0; d < s->max_depth; ++d) {
+        const int n_stepped = hybrid ? handover : s->max_depth;
+        for (int d = 0; d < n_stepped; ++d) {
             for (size_t k = 0; k < s->classes.size(); ++k) {
                 if (d >= s->cls_depth[k]) continue;
                 if (sky) {
-                    launch_rollouts_sky(s, s->classes[k], d, s->cls_stream[k]);
-                    launch_advance_sky(s, s->classes[k], d, s->cls_stream[k]);
+                    launch_rollouts_sky(s, s->classes[k], d, s->cls_stream[k], pdl);
+                    launch_advance_sky(s, s->classes[k], d, s->cls_stream[k], hybrid && d == n_stepped - 1, pdl);
                 } else {
-                    launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true);
-                    launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k]);
+                    launch_rollouts_class(s, s->classes[k], d, s->cls_stream[k], true, pdl && d > 0);
+                    launch_advance_class<false>(s, s->classes[k], d + 1, nullptr, s->cls_stream[k], pdl);
                 }
             }
         }
@@ -1114,6 +1206,15 @@ int bp_search_run(bp_search* s)
             BP_CUDA(cudaEventRecord(s->cls_done[k], s->cls_stream[k]));
             BP_CUDA(cudaStreamWaitEvent(s->ctx->stream, s->cls_done[k], 0));
         }
+        if (hybrid) {
+            // every chain has handed its live problems over: one launch plays what is left
+            dispatch_resident(s->variant, [&](auto MW, auto ME) {
+                ResidentVariant<decltype(MW)::value, decltype(ME)::value>::launch(s->grid_resident, s->ctx->stream,
+                                                                                   s->p, s->x);
+            });
+            s->ctx->launches++;
+            BP_CUDA(cudaGetLastError());
+        }
         return BP_OK;
     };
     // From the second run of a search on, the whole fork / launch / join sequence is one CUDA
@@ -1121,6 +1222,12 @@ int bp_search_run(bp_search* s)
     // the capture).  BP_GRAPH=0 keeps plain launches; the legacy NULL stream cannot be captured.
     static const bool graph_ok = !(getenv("BP_GRAPH") && atoi(getenv("BP_GRAPH")) == 0);
     s->n_runs++;
+    const int graph_key = hybrid ? 1 + handover : 0;
+    if (s->graph_exec && s->graph_key != graph_key) {          // the search changed form: capture again
+        cudaGraphExecDestroy(s->graph_exec);
+        s->graph_exec = nullptr;
+    }
+    s->graph_key = graph_key;
     if (graph_ok && s->ctx->stream != nullptr && (s->n_runs >= 2 || s->graph_exec)) {
         if (!s->graph_exec) {
             const int64_t before = s->ctx->launches;
@@ -1149,6 +1256,7 @@ int bp_search_run(bp_search* s)
         const int rc = issue();
         if (rc) return rc;
     }
+    s->ran_resident = hybrid;
     s->cur_depth = s->max_depth;
     return BP_OK;
 }
@@ -1183,6 +1291,29 @@ int bp_search_results(bp_search* s, bp_search_result* results, uint8_t* order, i
         BP_CUDA(cudaMemcpyAsync(child_scores, p.child_scores, P * (p.es / 2) * p.es * 4,
                                 cudaMemcpyDeviceToHost, st));
     BP_CUDA(cudaStreamSynchronize(st));
+#ifdef BP_TIMELINE
+    if (s->d_timeline && getenv("BP_TIMELINE_OUT")) {
+        const size_t n = (size_t)(MAX_DEPTHS + 1) * FS_CHAINS * 2;
+        std::vector<unsigned long long> h(n * 4);
+        BP_CUDA(cudaMemcpy(h.data(), s->d_timeline, n * 32, cudaMemcpyDeviceToHost));
+        unsigned long long base = ~0ull;
+        for (size_t i = 0; i < n; ++i)
+            if (h[4 * i + 3]) base = std::min(base, ~h[4 * i]);
+        if (FILE* f = fopen(getenv("BP_TIMELINE_OUT"), "w")) {
+            for (size_t k = 0; k < s->classes.size(); ++k)
+                fprintf(f, "{\"chain\": %d, \"problems\": %d, \"depths\": %d}\n", s->classes[k],
+                        s->cls_count[s->classes[k]], s->cls_depth[k]);
+            for (size_t i = 0; i < n; ++i)
+                if (h[4 * i + 3])
+                    fprintf(f, "{\"depth\": %d, \"chain\": %d, \"kind\": \"%s\", \"start_us\": %.2f, "
+                               "\"end_us\": %.2f, \"warp_us\": %.1f, \"warps\": %llu}\n",
+                            (int)(i / 2 / FS_CHAINS), (int)(i / 2 % FS_CHAINS), (i & 1) ? "advance" : "rollout",
+                            (~h[4 * i] - base) * 1e-3, (h[4 * i + 1] - base) * 1e-3, h[4 * i + 2] * 1e-3,
+                            h[4 * i + 3]);
+            fclose(f);
+        }
+    }
+#endif
     if (s->ran_resident) {
         // the resettable part of the queue header came back with the result block
         memcpy(reinterpret_cast<char*>(&s->h_queue) + RS_QUEUE_RESET_OFFSET, s->h_results.data(),

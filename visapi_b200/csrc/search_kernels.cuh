@@ -7,6 +7,32 @@
 
 namespace bp {
 
+// Debug build only (-DBP_TIMELINE, tools/timeline.py): every warp of a launch-per-depth kernel
+// stamps %globaltimer when it starts and when it leaves; per launch the host reads first start,
+// last end, the sum of warp lifetimes and the warp count -- which kernels overlap, how full the
+// GPU is in each, where a chain waits.  Not compiled into the shipped library.
+#ifdef BP_TIMELINE
+static __device__ unsigned long long* g_timeline;      // [launch id][4]
+struct TimelineScope {
+    int id;
+    unsigned long long t0;
+    __device__ __forceinline__ explicit TimelineScope(int launch_id) : id(launch_id), t0(global_timer_ns()) {}
+    __device__ __forceinline__ ~TimelineScope()
+    {
+        if ((threadIdx.x & 31) == 0 && g_timeline && id >= 0) {
+            const unsigned long long t1 = global_timer_ns();
+            atomicMax(&g_timeline[4 * id + 0], ~t0);
+            atomicMax(&g_timeline[4 * id + 1], t1);
+            atomicAdd(&g_timeline[4 * id + 2], t1 - t0);
+            atomicAdd(&g_timeline[4 * id + 3], 1ull);
+        }
+    }
+};
+#define BP_TIMELINE_SCOPE(launch_id) TimelineScope timeline_scope_(launch_id)
+#else
+#define BP_TIMELINE_SCOPE(launch_id)
+#endif
+
 // ------------------------------------------------------------------ rollout kernel
 // Persistent warps pull (child, chunk) tasks; a task builds the child board from its
 // parent (one placement) and plays CHUNK rollouts from it.
@@ -176,13 +202,20 @@ __global__ void __launch_bounds__(128)
 fs_rollout_lanes_kernel(SearchParams p, int cls, int cls_list_offset, int depth_slot, int half_units_per_warp,
                         int n_warps_full)
 {
+    BP_TIMELINE_SCOPE((depth_slot * FS_CHAINS + cls) * 2);
     __shared__ LaneTables<NB, W, EW> s_tb[4];
     __shared__ uint8_t s_sel8[256 * 8];
     fill_select_table(s_sel8);
     __syncthreads();
+    // (everything above overlaps the advance launch before this one; its child list is read below)
+    grid_dependency_wait();
+    const unsigned n_children = p.child_count[depth_slot * FS_CHAINS + cls];
+    // a block that is not needed (the blocks before it hold a warp for every 32-rollout chunk there
+    // is) leaves at once: the grid is sized for the children the depth CAN have
+    if ((unsigned long long)blockIdx.x * 4ull >= (unsigned long long)n_children * p.n_chunks) return;
+    grid_launch_dependents();              // the advance launch may take its (few) places now
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    const unsigned n_children = p.child_count[depth_slot * FS_CHAINS + cls];
     // Work unit = `group` consecutive 32-rollout chunks of ONE child: the problem's tables (shared
     // memory) and the child board (registers) are set up once per unit.  Units stay small
     // when there is little work (load balance) and grow up to a whole child when there is
@@ -650,6 +683,13 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
                   const int* __restrict__ cls_problems, int n_cls_problems, int next_slot,
                   const ChildStats* __restrict__ gathered)
 {
+    BP_TIMELINE_SCOPE(FIRST ? -1 : ((next_slot - 1) * FS_CHAINS + cls) * 2 + 1);
+    if (!FIRST) {
+        // the next depth's rollout launch may bring its blocks in (they fill their tables and wait
+        // for this launch to complete); this launch waits for the rollouts it scores
+        grid_launch_dependents();
+        grid_dependency_wait();
+    }
     __shared__ uint16_t cbuf[ADV_WARPS][32 * EJ];
     const int warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * ADV_WARPS + warp;

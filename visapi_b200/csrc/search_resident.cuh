@@ -423,6 +423,10 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
     load_state_cg(st, p.pstate + prob);
     const ProblemDesc d = p.desc[prob];
     uint32_t pw = __ldcg(p.planes + (size_t)prob * LANES_PLANE_STRIDE + lane);
+    // (resident: the problems still searching decide the next depth's unit size; asked for here so
+    // that the answer is back long before publish_units needs it)
+    const bool live_in_flight = sink.in_flight < 0;
+    int in_flight_seen = live_in_flight ? ld_volatile(&x.q->in_flight) : 0;   // (lanes may see different values)
     const int k0 = st.k, depth = st.depth, gpc = st.gpc;
 
     // ---- this rank's statistics per child: merge of the child's unit records -------------
@@ -445,8 +449,16 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
             c_tile[j] = t4.x | (t4.y << 8);
             c_pair[j] = reinterpret_cast<const uint4*>(p.pairs)[(size_t)prob * p.es + ent[j]];
             const uint4* rec = x.urec + (size_t)prob * x.urec_stride + (size_t)ci * gpc;
-#pragma unroll 2
-            for (int g = 0; g < gpc; ++g) merge_unit_rec(cs[j], __ldcg(rec + g));
+            // eight records in flight per trip to L2 (two at a time cost gpc / 2 dependent round
+            // trips: the larger part of the merge phase); an absent record merges as nothing
+            for (int g0 = 0; g0 < gpc; g0 += 8) {
+                uint4 r[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    r[i] = g0 + i < gpc ? __ldcg(rec + g0 + i) : make_uint4(NONE_U32, 0u, 0u, 0u);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) merge_unit_rec(cs[j], r[i]);
+            }
         }
     }
     if (p.n_ranks > 1) {
@@ -610,8 +622,7 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
     const long long t_committed = clock64();
     if (st.status == ST_ACTIVE) {
         p.planes[(size_t)prob * LANES_PLANE_STRIDE + lane] = pw;
-        if (sink.in_flight < 0)                                  // resident: the problems still searching
-            sink.in_flight = __shfl_sync(FULLMASK, ld_volatile(&x.q->in_flight), 0);
+        if (live_in_flight) sink.in_flight = max(1, __shfl_sync(FULLMASK, in_flight_seen, 0));
         publish_units(p, x, prob, st, sink);
     } else {
         finish_problem(p, prob, st);
@@ -919,8 +930,8 @@ fs_resident_seed_kernel(SearchParams p, ResidentParams x, UnitSink sink, const i
     st.placements_executed = p.placements_executed[prob];
     st.pad1 = 0;
     if (st.k == 0) return;
-    if (lane_id() == 0) atomicAdd(&x.q->in_flight, 1);
     if (sink.slots == nullptr) {                   // resident search: the unit queue of the problem's class
+        if (lane_id() == 0) atomicAdd(&x.q->in_flight, 1);
         const int qk = p.desc[prob].pad0;
         sink.tail = &x.q->cq[qk].tail;
         sink.slots = x.slots + x.ring_off[qk];
@@ -937,13 +948,23 @@ fs_resident_seed_kernel(SearchParams p, ResidentParams x, UnitSink sink, const i
 // warp-per-board advance that rebuilt every table at every depth.
 template <int NB, int W, int EW>
 __global__ void __launch_bounds__(128)
-fs_rollout_sky_kernel(SearchParams p, ResidentParams x, const unsigned long long* __restrict__ units,
-                      const unsigned long long* __restrict__ n_units_ptr, unsigned* __restrict__ counter)
+fs_rollout_sky_kernel(SearchParams p, ResidentParams x, const unsigned long long* units,
+                      const unsigned long long* n_units_ptr, unsigned* counter)
 {
+    BP_TIMELINE_SCOPE((int)(counter - p.task_counter) * 2);
     __shared__ LaneTables<NB, W, EW> s_tb[4];
     __shared__ uint8_t s_sel8[256 * 8];
     fill_select_table(s_sel8);
     __syncthreads();
+    grid_dependency_wait();                // (the table fill overlaps the advance launch before this one)
+    // a block that is not needed (the blocks before it hold a warp for every unit) leaves at once:
+    // the grid is sized for the units the depth CAN have, and late in a search most problems are
+    // finished
+    // (list and count are written by the launch before this one, which a programmatic dependent
+    // launch overlaps: read through L2, never by the non-coherent path a const __restrict__ load takes)
+    const unsigned long long n_units = __ldcg(n_units_ptr);
+    if ((unsigned long long)blockIdx.x * 4ull >= n_units) return;
+    grid_launch_dependents();
     PlayParams pp;
     pp.desc = p.desc; pp.pstate = p.pstate; pp.planes = p.planes; pp.wmask = p.wmask; pp.hmask = p.hmask;
     pp.pairs = reinterpret_cast<const uint4*>(p.pairs); pp.tile = p.tile; pp.ulist = x.ulist; pp.urec = x.urec;
@@ -951,23 +972,31 @@ fs_rollout_sky_kernel(SearchParams p, ResidentParams x, const unsigned long long
     pp.urec_stride = x.urec_stride; pp.seed = p.seed;
     const int lane = lane_id();
     const int warp = threadIdx.x >> 5;
-    const unsigned long long n_units = *n_units_ptr;
     int cached_prob = -1;
     for (;;) {
         unsigned unit = 0;
         if (lane == 0) unit = atomicAdd(counter, 1u);
         unit = __shfl_sync(FULLMASK, unit, 0);
         if (unit >= n_units) break;
-        const uint32_t payload = (uint32_t)(units[unit] >> 32);
+        const uint32_t payload = (uint32_t)(__ldcg(units + unit) >> 32);
         sky_play_unit<NB, W, EW>(pp, s_tb[warp], s_sel8, (int)(payload & ((1u << RS_PROBLEM_BITS) - 1u)),
                                  (int)(payload >> RS_PROBLEM_BITS), cached_prob);
     }
 }
 
-template <int UNUSED>
+// HANDOVER (hybrid form): the last launch-per-depth advance of a chain.  The problems that go on
+// are counted in the queue header and their units go to the unit queue of their class instead of
+// the chain's list: the resident kernel, launched when every chain has handed over, plays the
+// remaining depths.  `n_total` = problems of the whole search (unit size: the chain's share of the
+// active problems is taken for the whole batch's).
+template <int HANDOVER>
 __global__ void __launch_bounds__(ADV_WARPS * 32)
-fs_advance_sky_kernel(SearchParams p, ResidentParams x, UnitSink sink, const int* __restrict__ problems, int n)
+fs_advance_sky_kernel(SearchParams p, ResidentParams x, UnitSink sink, const int* __restrict__ problems, int n,
+                      int n_total)
 {
+    BP_TIMELINE_SCOPE(((int)(sink.active_next - p.child_count) - FS_CHAINS) * 2 + 1);
+    grid_launch_dependents();
+    grid_dependency_wait();
     __shared__ __align__(16) uint32_t s_scratch[ADV_WARPS][32];
     const int warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * ADV_WARPS + warp;
@@ -976,9 +1005,19 @@ fs_advance_sky_kernel(SearchParams p, ResidentParams x, UnitSink sink, const int
     const uint4 q1 = reinterpret_cast<const uint4*>(p.pstate + prob)[1];
     const uint4 q4 = reinterpret_cast<const uint4*>(p.pstate + prob)[4];
     if ((int)q4.z != ST_ACTIVE || p.status[prob] != ST_ACTIVE) return;
+    if (HANDOVER) {
+        const int qk = p.desc[prob].pad0;
+        sink.tail = &x.q->cq[qk].tail;
+        sink.slots = x.slots + x.ring_off[qk];
+        sink.mask = x.ring_mask[qk];
+        sink.in_flight = max(1, (int)(((long long)*sink.active_now * n_total) / n));
+        sink.active_now = nullptr;
+    }
     long long c_exch = 0, phase[3] = {0, 0, 0};
-    if ((int)q1.y <= 32) server_advance_core<1>(p, x, prob, sink, c_exch, phase, s_scratch[warp]);
-    else server_advance_core<4>(p, x, prob, sink, c_exch, phase, s_scratch[warp]);
+    int status;
+    if ((int)q1.y <= 32) status = server_advance_core<1>(p, x, prob, sink, c_exch, phase, s_scratch[warp]);
+    else status = server_advance_core<4>(p, x, prob, sink, c_exch, phase, s_scratch[warp]);
+    if (HANDOVER && status == ST_ACTIVE && lane_id() == 0) atomicAdd(&x.q->in_flight, 1);
 }
 
 }  // namespace bp

@@ -104,6 +104,14 @@ struct SearchParams {
     ProbState* pstate;       // [P]
 };
 
+// Programmatic dependent launch (the launch-per-depth chains, flat_search.cu): a kernel launched with
+// the attribute may start while the kernel before it in the stream is still running.  It must not
+// touch what that kernel writes before grid_dependency_wait() (returns when the previous kernel
+// has completed and its writes are visible; a no-op in a plain launch); the previous kernel lets
+// it start with grid_launch_dependents() (else: when its blocks exit).
+__device__ __forceinline__ void grid_dependency_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // loads of state another warp of the SAME launch may have written: through L2 (ld.global.cg),
 // never from this SM's L1
 template <bool CG, typename T>
