@@ -113,7 +113,7 @@ def parse_args():
                     help="seconds of the python-port CPU sample (0 = skip cpu_baseline)")
     ap.add_argument("--ref-budget", type=float, default=10.0,
                     help="--impl reference: seconds per step")
-    ap.add_argument("--mode", default="auto", choices=["auto", "stepped", "resident"],
+    ap.add_argument("--mode", default="auto", choices=["auto", "stepped", "resident", "hybrid"],
                     help="stepped: one rollout + one advance launch per depth and class; "
                          "resident: one launch per shape class runs every depth; auto: stepped")
     ap.add_argument("--no-e2e", action="store_true")
@@ -491,7 +491,9 @@ def our_arm(a):
     ms_rank = ev0.elapsed_time(ev1)
     clocks = sampler.stop(t_wall0, t_wall0 + wall)
     res = search.results()
-    resident = search.last_run_resident()
+    search_form = search.last_run_form()
+    resident = search_form == "resident"
+    sky_kernels = search.last_run_skyline()
 
     ms_max = reduce_max(ms_rank)
     ms_min = -reduce_max(-ms_rank)
@@ -596,7 +598,8 @@ def our_arm(a):
     roofline = {
         "bound": "issue",
         "kernel": ("fs_search_resident_kernel" if resident else
-                   ("fs_rollout_lanes_kernel" if lane_kernel else "fs_rollout_kernel")),
+                   (("fs_rollout_sky_kernel" if sky_kernels else "fs_rollout_lanes_kernel")
+                    if lane_kernel else "fs_rollout_kernel")),
         "achieved": achieved / 1e9, "peak": issue_peak / 1e9, "unit": "Gwarp-inst/s",
         "frac": achieved / issue_peak,
         "frac_min_ops": (min_inst / sec_rank / issue_peak) if min_inst else None,
@@ -712,7 +715,7 @@ def our_arm(a):
                             "the whole set searched on one GPU" if shard_equals_full else ""),
             "shard_equals_single_gpu": shard_equals_full,
             "problems_per_step": P, "wall_s_per_step": wall / a.steps,
-            "ms_per_step_fastest_rank": ms_min / a.steps, "search_mode": "resident" if resident else "stepped",
+            "ms_per_step_fastest_rank": ms_min / a.steps, "search_mode": search_form,
             "clocks": clocks, "gpu_launches": int(launches_all),
             "roofline": roofline, "e2e": e2e, "weak": weak, "cpu_baseline": cpu,
         }

@@ -168,7 +168,8 @@ int bp_search_reset(bp_search *s);
  *                       forms when the hand-over depth is the first or the last one;
  *   BP_SEARCH_AUTO      the fastest of these as measured on B200.
  * The environment variable BP_SEARCH=stepped|resident|hybrid overrides the mode.
- * bp_search_last_run: 0 = launch-per-depth, 1 = resident, 2 = hybrid. */
+ * bp_search_last_run: 0 = launch-per-depth (warp-per-board advance, rebuilt tables), 1 = resident,
+ * 2 = hybrid, 3 = launch-per-depth on the skyline state (the resident kernel's playout and advance). */
 typedef enum { BP_SEARCH_AUTO = 0, BP_SEARCH_STEPPED = 1, BP_SEARCH_RESIDENT = 2, BP_SEARCH_HYBRID = 3 } bp_search_mode;
 int bp_search_set_mode(bp_search *s, int mode);
 /* on != 0: time the launches of the next run with CUDA events on the context's stream, shape

@@ -607,25 +607,27 @@ def test_every_problem_of_both_sets_exact_at_n100(eng):
 
 
 def test_auto_mode_follows_the_measured_rule(eng):
-    """AUTO (flat_search.cu default_mode): one large instance (a long chain of moves with little
-    work each, the 50-tile root-parallel workload) takes the resident kernel; a batch of 20-tile
-    problems takes the launch-per-depth form.  Both equal the C oracle."""
+    """AUTO (flat_search.cu default_mode): one large instance with many rollouts per child (a long
+    chain of moves, the 50-tile root-parallel workload) takes the resident kernel; the same instance
+    with few rollouts and a batch of 20-tile problems take the launch-per-depth form.  All equal the
+    C oracle."""
     import random
     from visapi_b200 import datasets, pack_tiles
     from visapi_b200.data_generator import DataGenerator
     random.seed(7)
     tiles, board = DataGenerator().gen_tiles_and_board(50, 30, 30, order_tiles=True)
     tiles = [tuple(int(v) for v in t) for t in tiles]
-    s = eng.search([30], [30], pack_tiles([tiles]), [len(tiles)], 24, 0, 123, [5])
-    s.reset()
-    s.run()
-    got = s.results()
-    assert s.last_run_resident()
-    s.close()
-    want = c_oracle.flat_search(tiles, np.zeros((30, 30), dtype=np.int64), 24, "max_depth", 123, 5)
-    assert int(got["depth"][0]) == want["depth"] and int(got["rollouts"][0]) == want["rollouts"]
-    assert int(got["n_tiles_placed"][0]) == want["n_tiles_placed"]
-    assert got["order"][0, :got["n_order"][0]].tolist() == want["solution_tiles_order"]
+    for n_sim, form in ((520, "resident"), (24, "stepped")):
+        s = eng.search([30], [30], pack_tiles([tiles]), [len(tiles)], n_sim, 0, 123, [5])
+        s.reset()
+        s.run()
+        got = s.results()
+        assert s.last_run_form() == form
+        s.close()
+        want = c_oracle.flat_search(tiles, np.zeros((30, 30), dtype=np.int64), n_sim, "max_depth", 123, 5)
+        assert int(got["depth"][0]) == want["depth"] and int(got["rollouts"][0]) == want["rollouts"]
+        assert int(got["n_tiles_placed"][0]) == want["n_tiles_placed"]
+        assert got["order"][0, :got["n_order"][0]].tolist() == want["solution_tiles_order"]
 
     probs = datasets.load_problem_set("g")[:6]
     batch = datasets.batch_arrays(probs)

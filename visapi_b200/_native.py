@@ -421,7 +421,13 @@ class Search(object):
         """"stepped" | "resident" | "hybrid": how the last bp_search_run played the search."""
         r = C.c_int()
         self.engine._check(self._lib.bp_search_last_run(self._h, C.byref(r)))
-        return ("stepped", "resident", "hybrid")[r.value]
+        return ("stepped", "resident", "hybrid", "stepped")[r.value]
+
+    def last_run_skyline(self):
+        """True when the last run's launch-per-depth part used the skyline kernels."""
+        r = C.c_int()
+        self.engine._check(self._lib.bp_search_last_run(self._h, C.byref(r)))
+        return r.value in (2, 3)
 
     def last_run_resident(self):
         return self.last_run_form() == "resident"

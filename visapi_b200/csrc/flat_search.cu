@@ -380,6 +380,8 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             static const bool no_affinity = getenv("BP_RESIDENT_AFFINITY") && atoi(getenv("BP_RESIDENT_AFFINITY")) == 0;
             if (no_affinity) std::fill(s->h_home.begin(), s->h_home.end(), 0);
         }
+        s->x.poll_ns = getenv("BP_RESIDENT_POLL_NS") ? std::max(32, atoi(getenv("BP_RESIDENT_POLL_NS"))) : 256;
+        s->x.poll_tier = getenv("BP_RESIDENT_POLL_TIER") ? std::max(0, atoi(getenv("BP_RESIDENT_POLL_TIER"))) : 0;
         double upw = 4.0;
         if (const char* env = getenv("BP_RESIDENT_UPW")) upw = atof(env);
         s->x.units_per_warp_x4 = std::max(1, (int)(4.0 * upw + 0.5));
@@ -777,7 +779,10 @@ static bool sky_stepped_ok(const bp_search* s)
         if (strcmp(env, "legacy") == 0) return false;
         if (strcmp(env, "sky") == 0) return true;
     }
-    return s->p.n_chunks <= 8;
+    // (with programmatic dependent launches, profiles/r2/pdl_sweep.txt: 125 problems at N = 1000 take
+    // 1.87 ms on the skyline kernels against 1.97 ms, 250 take 3.15 / 3.29, 500 take 5.92 / 5.87, the
+    // full set 11.27 / 11.17; 125 Braam instances 2.90 / 3.27)
+    return s->p.n_chunks <= 8 || s->p.n_problems <= 384;
 }
 static int sky_upw_x4()
 {
@@ -891,6 +896,7 @@ int bp_search_reset(bp_search* s)
     launch_advance<true>(s, 0, nullptr);
     BP_CUDA(cudaGetLastError());
     s->ran_resident = false;
+    s->sky_stepped = false;
     s->cur_depth = 0;
     s->ev_depths = 0;
     s->ready = true;
@@ -1012,7 +1018,7 @@ int bp_search_info(bp_search* s, int* lane_kernel, int* n_classes)
 int bp_search_last_run(bp_search* s, int* resident)
 {
     BP_REQUIRE(s && resident, "null argument");
-    *resident = s->ran_resident ? (s->hybrid_depths > 0 ? 2 : 1) : 0;
+    *resident = s->ran_resident ? (s->hybrid_depths > 0 ? 2 : 1) : (s->sky_stepped ? 3 : 0);
     return BP_OK;
 }
 
@@ -1049,19 +1055,20 @@ int bp_search_max_depth(bp_search* s, int* max_depth)
     return BP_OK;
 }
 
-// AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt, root_parallel_*.json,
-// DESIGN.md section 4).  With the grid bound, the CUDA graph and the skyline advance kernel the
-// launch-per-depth form wins every batch of 20-tile problems from 1 to 1000 at N = 100 and 1000
-// (0.27 / 0.31 ms for one instance, 1.97 / 2.10 ms for 125, 11.2 / 12.3 ms for 1000), because its
-// per-class kernels run ~6 % fewer instructions and give no SM to server warps.  The resident
-// kernel wins where a search is a long chain of moves with little work each: one large instance
-// (50 tiles: 4.90 / 5.23 ms at N = 5000, 45.7 / 73.1 ms at N = 100 000), and it is the only form that
-// runs a partitioned (root-parallel) search without a host step per move.
+// AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt, c4_modes.txt, DESIGN.md
+// section 4).  With programmatic dependent launches, the grid bound, the CUDA graph and the skyline
+// kernels the launch-per-depth form wins every batch of 20-tile problems from 1 to 1000 at N = 100
+// and 1000 (0.22 / 0.32 ms for one instance, 1.81 / 2.09 ms for 125, 11.1 / 12.4 ms for 1000): its
+// per-class kernels run ~6 % fewer instructions and give no SM to server warps.  The resident kernel
+// wins where a search is a long chain of moves on one or a few instances with many rollouts per
+// child (50 tiles: 5.0 / 6.2 ms at N = 5000, 2.14 / 2.21 ms at N = 1000, but 1.24 / 1.00 ms at N = 100),
+// and it is the only form that runs a partitioned (root-parallel) search without a host step per move.
 static int default_mode(const bp_search* s)
 {
     if (!s->ring_cap) return BP_SEARCH_STEPPED;
     if (s->p.n_ranks > 1) return BP_SEARCH_RESIDENT;
-    return (s->p.n_problems <= 4 && s->max_depth > 32) ? BP_SEARCH_RESIDENT : BP_SEARCH_STEPPED;
+    return (s->p.n_problems <= 4 && s->max_depth > 32 && s->p.n_chunks >= 16) ? BP_SEARCH_RESIDENT
+                                                                               : BP_SEARCH_STEPPED;
 }
 
 int bp_search_run(bp_search* s)
@@ -1147,8 +1154,10 @@ int bp_search_run(bp_search* s)
         return BP_OK;
     }
     const bool hybrid = mode == BP_SEARCH_HYBRID;
-    if (!hybrid && (s->profiling || s->classes.size() == 1 || getenv("BP_SERIAL_CLASSES"))) {
+    static const bool fork_single = !(getenv("BP_FORK_SINGLE") && atoi(getenv("BP_FORK_SINGLE")) == 0);
+    if (!hybrid && (s->profiling || (s->classes.size() == 1 && !fork_single) || getenv("BP_SERIAL_CLASSES"))) {
         s->in_profiled_run = s->profiling;
+        s->sky_stepped = false;
         int rc = BP_OK;
         while (!rc && s->cur_depth < s->max_depth) {
             rc = bp_search_step_rollouts(s);

@@ -82,6 +82,7 @@ struct ResidentParams {
     unsigned done_mask;
     int n_server_sms;            // the first n_server_sms SMs to receive a block advance problems, the others play
     int n_roll_warps;            // warps that play (sizes the work units)
+    int poll_ns, poll_tier;      // rollout warps' poll back-off: cap (ns), warps per tier (0: one tier)
     // root-parallel exchange over peer memory (n_ranks > 1): every rank's buffers, own included.
     // The pointers live in a small device table, not in the parameter block: indexing a parameter
     // array with a run-time rank would move the whole block into local memory.

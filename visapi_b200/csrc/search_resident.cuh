@@ -423,10 +423,6 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
     load_state_cg(st, p.pstate + prob);
     const ProblemDesc d = p.desc[prob];
     uint32_t pw = __ldcg(p.planes + (size_t)prob * LANES_PLANE_STRIDE + lane);
-    // (resident: the problems still searching decide the next depth's unit size; asked for here so
-    // that the answer is back long before publish_units needs it)
-    const bool live_in_flight = sink.in_flight < 0;
-    int in_flight_seen = live_in_flight ? ld_volatile(&x.q->in_flight) : 0;   // (lanes may see different values)
     const int k0 = st.k, depth = st.depth, gpc = st.gpc;
 
     // ---- this rank's statistics per child: merge of the child's unit records -------------
@@ -449,16 +445,11 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
             c_tile[j] = t4.x | (t4.y << 8);
             c_pair[j] = reinterpret_cast<const uint4*>(p.pairs)[(size_t)prob * p.es + ent[j]];
             const uint4* rec = x.urec + (size_t)prob * x.urec_stride + (size_t)ci * gpc;
-            // eight records in flight per trip to L2 (two at a time cost gpc / 2 dependent round
-            // trips: the larger part of the merge phase); an absent record merges as nothing
-            for (int g0 = 0; g0 < gpc; g0 += 8) {
-                uint4 r[8];
-#pragma unroll
-                for (int i = 0; i < 8; ++i)
-                    r[i] = g0 + i < gpc ? __ldcg(rec + g0 + i) : make_uint4(NONE_U32, 0u, 0u, 0u);
-#pragma unroll
-                for (int i = 0; i < 8; ++i) merge_unit_rec(cs[j], r[i]);
-            }
+            // (two records per trip to L2.  Measured: eight per trip, predicated, is 1.5 % faster on a
+            // 50-tile instance at N = 5000 and 15-25 % SLOWER on small searches at N = 100; four per
+            // trip is slower on both -- profiles/r2/ab_merge_batch.txt)
+#pragma unroll 2
+            for (int g = 0; g < gpc; ++g) merge_unit_rec(cs[j], __ldcg(rec + g));
         }
     }
     if (p.n_ranks > 1) {
@@ -622,7 +613,8 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
     const long long t_committed = clock64();
     if (st.status == ST_ACTIVE) {
         p.planes[(size_t)prob * LANES_PLANE_STRIDE + lane] = pw;
-        if (live_in_flight) sink.in_flight = max(1, __shfl_sync(FULLMASK, in_flight_seen, 0));
+        if (sink.in_flight < 0)                                  // resident: the problems still searching
+            sink.in_flight = __shfl_sync(FULLMASK, ld_volatile(&x.q->in_flight), 0);
         publish_units(p, x, prob, st, sink);
     } else {
         finish_problem(p, prob, st);
@@ -690,6 +682,13 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
     long long phase[3] = {0, 0, 0};
     unsigned n_played = 0, n_adv = 0, n_polls = 0;
     const unsigned n_roll_warps = (unsigned)x.n_roll_warps;
+    // longest sleep between two polls of a rollout warp that finds no unit: the warps of the
+    // first blocks poll often (they take the units of a thin depth at once), the later blocks'
+    // warps sleep longer, so that a few hundred pollers, not several thousand, hammer the queue
+    // heads while little work is in flight
+    const unsigned poll_cap = x.poll_tier > 0
+        ? (unsigned)x.poll_ns << min(4u, (blockIdx.x * 4u + (threadIdx.x >> 5)) / (unsigned)x.poll_tier)
+        : (unsigned)x.poll_ns;
     // Role of this block: the first n_server_sms SMs that receive a block of the launch become
     // server SMs (every block placed there advances problems), elected by arrival so that the
     // election does not depend on how %smid is numbered or on what else runs on the device.
@@ -777,7 +776,7 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
                         if (ld_volatile(&q->in_flight) <= 0 || ld_volatile(&q->abort)) break;
                         ++n_polls;
                         __nanosleep(ns);
-                        if (ns < 256) ns *= 2;
+                        if (ns < poll_cap) ns *= 2;
                         else {
                             const unsigned long long now = global_timer_ns();
                             if (t_begin == 0) t_begin = now;
@@ -789,7 +788,7 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
                 if (ld_volatile(&q->in_flight) <= 0 || ld_volatile(&q->abort)) break;
                 ++n_polls;
                 __nanosleep(ns);
-                if (ns < 256) ns *= 2;
+                if (ns < poll_cap) ns *= 2;
                 else {
                     const unsigned long long now = global_timer_ns();
                     if (t_begin == 0) t_begin = now;
