@@ -725,7 +725,13 @@ static void launch_advance_class(bp_search* s, int c, int next_slot, const Child
 template <bool FIRST>
 static void launch_advance(bp_search* s, int next_slot, const ChildStats* gathered)
 {
-    for (int c : s->classes) launch_advance_class<FIRST>(s, c, next_slot, gathered, s->ctx->stream);
+    // (the first advances of a reset overlap: every class after the first is a dependent launch)
+    static const bool pdl = !(getenv("BP_PDL") && atoi(getenv("BP_PDL")) == 0);
+    bool first = true;
+    for (int c : s->classes) {
+        launch_advance_class<FIRST>(s, c, next_slot, gathered, s->ctx->stream, FIRST && pdl && !first);
+        first = false;
+    }
 }
 
 // `overlapped`: other classes' launches run beside this one on their own streams.  Measured on

@@ -684,18 +684,20 @@ fs_advance_kernel(SearchParams p, int cls, int cls_list_offset,
                   const ChildStats* __restrict__ gathered)
 {
     BP_TIMELINE_SCOPE(FIRST ? -1 : ((next_slot - 1) * FS_CHAINS + cls) * 2 + 1);
-    if (!FIRST) {
-        // the next depth's rollout launch may bring its blocks in (they fill their tables and wait
-        // for this launch to complete); this launch waits for the rollouts it scores
-        grid_launch_dependents();
-        grid_dependency_wait();
-    }
+    // !FIRST: the next depth's rollout launch may bring its blocks in (they fill their tables and
+    // wait for this launch to complete); this launch waits for the rollouts it scores.
+    // FIRST (bp_search_reset): the classes' launches are independent of each other, so each lets the
+    // next one start at once and they run side by side on the one stream; each waits for its
+    // predecessor only before it ENDS, so that the last one's completion still means all are done.
+    grid_launch_dependents();
+    if (!FIRST) grid_dependency_wait();
     __shared__ uint16_t cbuf[ADV_WARPS][32 * EJ];
     const int warp = threadIdx.x >> 5;
     const int idx = blockIdx.x * ADV_WARPS + warp;
-    if (idx >= n_cls_problems) return;
-    advance_problem<RHO, W, EJ, FIRST>(p, cls_problems[idx], cls, cls_list_offset, next_slot, gathered,
-                                       cbuf[warp]);
+    if (idx < n_cls_problems)
+        advance_problem<RHO, W, EJ, FIRST>(p, cls_problems[idx], cls, cls_list_offset, next_slot, gathered,
+                                           cbuf[warp]);
+    if (FIRST) grid_dependency_wait();
 }
 
 }  // namespace bp
