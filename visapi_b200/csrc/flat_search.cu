@@ -451,6 +451,7 @@ static int search_create(bp_context* ctx, int n_problems, const int32_t* rows, c
             TRY(dev_alloc(s, &p.alive, P));
             s->x.urec_stride = std::min(p.es * s->x.gpc_max, (int)RS_MAX_UNITS);
             TRY(dev_alloc(s, &s->x.urec, P * (size_t)s->x.urec_stride));
+            TRY(dev_alloc(s, &s->x.cacc, P * (size_t)p.es));
             TRY(dev_alloc(s, &s->x.ulist, P * p.es));
             TRY(dev_alloc(s, &p.pstate, P));
             TRY(dev_alloc(s, &s->x.slots, s->ring_cap));

@@ -77,6 +77,12 @@ struct ResidentParams {
     uint8_t* ulist;              // [P][ES] legal entries of the current depth, in table order
     uint4* urec;                 // [P][urec_stride] one 16-byte record per unit of the current depth
     int urec_stride;
+    // [P][ES] per child (rank among the legal entries) of the current depth: x = max placements,
+    // y = first solved rollout (NONE_U32), z / w = placements of all rollouts (64 bits).  Every
+    // unit folds its statistics in with three reductions at L2 (max, min and sum do not depend on
+    // the order), so the advance reads ONE record per child instead of merging the child's unit
+    // records in order; only a child with a solved rollout still needs them (its prefix count).
+    uint4* cacc;
     // problems whose depth has been played, waiting for a server warp (slot = problem << 32 | ticket + 1)
     unsigned long long* done_slots;
     unsigned done_mask;
@@ -231,6 +237,8 @@ __device__ __forceinline__ void publish_units(const SearchParams& p, const Resid
             base += __popc(st.legal[j]);
         }
     }
+    for (int ci = lane; ci < st.k; ci += 32)                     // the children's accumulators, empty
+        x.cacc[(size_t)prob * p.es + ci] = make_uint4(0u, NONE_U32, 0u, 0u);
     // units per child: enough units that the problems in flight offer units_per_warp units to
     // every resident warp, no more than gpc_max (ring capacity) and RS_MAX_UNITS per problem
     const unsigned uk = (unsigned)st.k, nc = (unsigned)p.n_chunks;

@@ -116,6 +116,7 @@ struct PlayParams {
     const uint4* tile;
     const uint8_t* ulist;
     uint4* urec;
+    uint4* cacc;
     int es, n_chunks, n_local, sim_begin, urec_stride;
     uint32_t seed;
 };
@@ -212,7 +213,14 @@ __device__ __forceinline__ void sky_play_unit(const PlayParams& p, LaneTables<NB
             }
         }
     }
-    if (lane == 0) G(p.urec)[(size_t)prob * p.urec_stride + uidx] = pack_unit_rec(u);
+    if (lane == 0) {
+        G(p.urec)[(size_t)prob * p.urec_stride + uidx] = pack_unit_rec(u);
+        // ... and folded into the child's accumulator (ResidentParams::cacc)
+        uint4* acc = G(p.cacc) + (size_t)prob * p.es + ci;
+        atomicMax(&acc->x, (uint32_t)u.max_steps);
+        if (u.first_solved != NONE_U32) atomicMin(&acc->y, u.first_solved);
+        atomicAdd(reinterpret_cast<unsigned long long*>(&acc->z), (unsigned long long)u.sum_steps);
+    }
 }
 
 // ---- root-parallel: per-child statistics of this rank to every rank, then wait for all -----
@@ -444,12 +452,21 @@ __device__ __forceinline__ int server_advance_core(const SearchParams& p, const 
             const uint4 t4 = p.tile[(size_t)prob * p.es + ent[j]];
             c_tile[j] = t4.x | (t4.y << 8);
             c_pair[j] = reinterpret_cast<const uint4*>(p.pairs)[(size_t)prob * p.es + ent[j]];
-            const uint4* rec = x.urec + (size_t)prob * x.urec_stride + (size_t)ci * gpc;
-            // (two records per trip to L2.  Measured: eight per trip, predicated, is 1.5 % faster on a
-            // 50-tile instance at N = 5000 and 15-25 % SLOWER on small searches at N = 100; four per
-            // trip is slower on both -- profiles/r2/ab_merge_batch.txt)
-#pragma unroll 2
-            for (int g = 0; g < gpc; ++g) merge_unit_rec(cs[j], __ldcg(rec + g));
+            // the child's statistics: one accumulator record (every unit folded itself in); the
+            // placements up to a solved rollout need the unit records in order -- only for a child
+            // that has one, i.e. at most once per problem
+            const uint4 a = __ldcg(x.cacc + (size_t)prob * p.es + ci);
+            cs[j].max_steps = (int)a.x;
+            cs[j].first_solved = a.y;
+            cs[j].sum_steps = (long long)((unsigned long long)a.z | ((unsigned long long)a.w << 32));
+            cs[j].prefix_steps = cs[j].sum_steps;
+            if (a.y != NONE_U32) {
+                const uint4* rec = x.urec + (size_t)prob * x.urec_stride + (size_t)ci * gpc;
+                ChildStats t;
+                t.max_steps = 0; t.first_solved = NONE_U32; t.sum_steps = 0; t.prefix_steps = 0;
+                for (int g = 0; g < gpc; ++g) merge_unit_rec(t, __ldcg(rec + g));
+                cs[j].prefix_steps = t.prefix_steps;
+            }
         }
     }
     if (p.n_ranks > 1) {
@@ -668,7 +685,7 @@ fs_search_resident_kernel(SearchParams p, ResidentParams x)
         s_pp.desc = p.desc; s_pp.pstate = p.pstate;
         s_pp.planes = p.planes; s_pp.wmask = p.wmask; s_pp.hmask = p.hmask;
         s_pp.pairs = reinterpret_cast<const uint4*>(p.pairs); s_pp.tile = p.tile;
-        s_pp.ulist = x.ulist; s_pp.urec = x.urec;
+        s_pp.ulist = x.ulist; s_pp.urec = x.urec; s_pp.cacc = x.cacc;
         s_pp.es = p.es; s_pp.n_chunks = p.n_chunks; s_pp.n_local = p.n_local;
         s_pp.sim_begin = p.sim_begin; s_pp.urec_stride = x.urec_stride; s_pp.seed = p.seed;
     }
@@ -966,7 +983,7 @@ fs_rollout_sky_kernel(SearchParams p, ResidentParams x, const unsigned long long
     grid_launch_dependents();
     PlayParams pp;
     pp.desc = p.desc; pp.pstate = p.pstate; pp.planes = p.planes; pp.wmask = p.wmask; pp.hmask = p.hmask;
-    pp.pairs = reinterpret_cast<const uint4*>(p.pairs); pp.tile = p.tile; pp.ulist = x.ulist; pp.urec = x.urec;
+    pp.pairs = reinterpret_cast<const uint4*>(p.pairs); pp.tile = p.tile; pp.ulist = x.ulist; pp.urec = x.urec; pp.cacc = x.cacc;
     pp.es = p.es; pp.n_chunks = p.n_chunks; pp.n_local = p.n_local; pp.sim_begin = p.sim_begin;
     pp.urec_stride = x.urec_stride; pp.seed = p.seed;
     const int lane = lane_id();
