@@ -624,8 +624,8 @@ def our_arm(a):
             "serialised_rollout_ms": rollout_ms, "serialised_advance_ms": advance_ms,
             "rollout_share": rollout_ms / max(rollout_ms + advance_ms, 1e-9),
             "frac": algo_inst / (rollout_ms / 1e3) / issue_peak},
-        "ncu_in_flight_share": {"rollout_kernels": 0.916, "advance_kernels": 0.080,
-                                "source": "profiles/r1/launches_r1_final.csv (launch list of this command)"},
+        "ncu_in_flight_share": {"rollout_kernels": 0.919, "advance_kernels": 0.075,
+                                "source": "profiles/r2/launches_r2_final.csv (launch list of this command)"},
         "launches_per_step": ({"resident": 1, "seed": 1} if resident
                               else {"rollout": n_launches, "advance": n_launches}),
         "placements_executed_per_step_this_rank": float(res_p["placements_executed"].sum()),

@@ -607,27 +607,39 @@ def test_every_problem_of_both_sets_exact_at_n100(eng):
 
 
 def test_auto_mode_follows_the_measured_rule(eng):
-    """AUTO (flat_search.cu default_mode): one large instance with many rollouts per child (a long
-    chain of moves, the 50-tile root-parallel workload) takes the resident kernel; the same instance
-    with few rollouts and a batch of 20-tile problems take the launch-per-depth form.  All equal the
-    C oracle."""
+    """AUTO (flat_search.cu default_mode): one large instance with very many rollouts per child (a
+    long chain of moves, the 50-tile root-parallel workload) takes the resident kernel; the same
+    instance with few rollouts and a batch of 20-tile problems take the launch-per-depth form."""
     import random
     from visapi_b200 import datasets, pack_tiles
     from visapi_b200.data_generator import DataGenerator
     random.seed(7)
     tiles, board = DataGenerator().gen_tiles_and_board(50, 30, 30, order_tiles=True)
     tiles = [tuple(int(v) for v in t) for t in tiles]
-    for n_sim, form in ((520, "resident"), (24, "stepped")):
-        s = eng.search([30], [30], pack_tiles([tiles]), [len(tiles)], n_sim, 0, 123, [5])
+    s = eng.search([30], [30], pack_tiles([tiles]), [len(tiles)], 24, 0, 123, [5])
+    s.reset()
+    s.run()
+    got = s.results()
+    assert s.last_run_form() == "stepped"
+    s.close()
+    want = c_oracle.flat_search(tiles, np.zeros((30, 30), dtype=np.int64), 24, "max_depth", 123, 5)
+    assert int(got["depth"][0]) == want["depth"] and int(got["rollouts"][0]) == want["rollouts"]
+    assert int(got["n_tiles_placed"][0]) == want["n_tiles_placed"]
+    assert got["order"][0, :got["n_order"][0]].tolist() == want["solution_tiles_order"]
+    # many rollouts per child: AUTO takes the resident kernel, and it returns what the
+    # launch-per-depth form returns
+    outs = {}
+    for mode in ("auto", "stepped"):
+        s = eng.search([30], [30], pack_tiles([tiles]), [len(tiles)], 2100, 0, 123, [5])
+        s.set_mode(mode)
         s.reset()
         s.run()
-        got = s.results()
-        assert s.last_run_form() == form
+        outs[mode] = s.results(want_scores=True)
+        assert s.last_run_form() == ("resident" if mode == "auto" else "stepped")
         s.close()
-        want = c_oracle.flat_search(tiles, np.zeros((30, 30), dtype=np.int64), n_sim, "max_depth", 123, 5)
-        assert int(got["depth"][0]) == want["depth"] and int(got["rollouts"][0]) == want["rollouts"]
-        assert int(got["n_tiles_placed"][0]) == want["n_tiles_placed"]
-        assert got["order"][0, :got["n_order"][0]].tolist() == want["solution_tiles_order"]
+    for k in ("depth", "solution_found", "n_tiles_placed", "rollouts", "rollout_placements", "order", "path",
+              "child_scores"):
+        np.testing.assert_array_equal(outs["auto"][k], outs["stepped"][k], err_msg=k)
 
     probs = datasets.load_problem_set("g")[:6]
     batch = datasets.batch_arrays(probs)

@@ -774,11 +774,12 @@ static void launch_rollouts_class(bp_search* s, int c, int depth, cudaStream_t s
 }
 
 // ---- launch-per-depth form on the skyline state (search_resident.cuh) ------------------------
-// Measured (profiles/r2/shard_sweep_sky.txt): with few rollouts per child a depth is little work and
-// the advance launch between two depths is what the chain waits for -- the skyline advance takes
-// 0.67 / 2.07 ms where the warp-per-board advance takes 0.73 / 2.13 ms (125 / 1000 problems,
-// N = 100); with N = 1000 the rollouts dominate and the older pair of kernels is 1.5 % faster
-// (11.25 against 11.45 ms per set).  BP_STEPPED=sky|legacy forces one of them.
+// The resident kernel's playout and advance with launches as barriers.  The advance is the compact
+// skyline advance (no table is rebuilt) and, since the units fold their statistics into one
+// accumulator per child, it reads one record per child: with dependent launches this pair of
+// kernels is faster than the warp-per-board advance with per-depth tables at every size measured
+// (profiles/r2/sky_vs_legacy_final.txt: 125 problems 1.79 / 1.92 ms, 500 problems 5.61 / 5.86 ms, the full
+// set 10.89 / 11.17 ms at N = 1000).  BP_STEPPED=sky|legacy forces one of them.
 static bool sky_stepped_ok(const bp_search* s)
 {
     if (!(s->ring_cap != 0 && s->p.use_lanes && s->p.n_ranks == 1)) return false;
@@ -786,10 +787,7 @@ static bool sky_stepped_ok(const bp_search* s)
         if (strcmp(env, "legacy") == 0) return false;
         if (strcmp(env, "sky") == 0) return true;
     }
-    // (with programmatic dependent launches, profiles/r2/pdl_sweep.txt: 125 problems at N = 1000 take
-    // 1.87 ms on the skyline kernels against 1.97 ms, 250 take 3.15 / 3.29, 500 take 5.92 / 5.87, the
-    // full set 11.27 / 11.17; 125 Braam instances 2.90 / 3.27)
-    return s->p.n_chunks <= 8 || s->p.n_problems <= 384;
+    return true;
 }
 static int sky_upw_x4()
 {
@@ -1065,16 +1063,17 @@ int bp_search_max_depth(bp_search* s, int* max_depth)
 // AUTO: the form measured faster on B200 (profiles/r2/auto_threshold.txt, c4_modes.txt, DESIGN.md
 // section 4).  With programmatic dependent launches, the grid bound, the CUDA graph and the skyline
 // kernels the launch-per-depth form wins every batch of 20-tile problems from 1 to 1000 at N = 100
-// and 1000 (0.22 / 0.32 ms for one instance, 1.81 / 2.09 ms for 125, 11.1 / 12.4 ms for 1000): its
+// and 1000 (0.18 / 0.28 ms for one instance, 1.79 / 2.1 ms for 125, 10.9 / 12.4 ms for 1000): its
 // per-class kernels run ~6 % fewer instructions and give no SM to server warps.  The resident kernel
-// wins where a search is a long chain of moves on one or a few instances with many rollouts per
-// child (50 tiles: 5.0 / 6.2 ms at N = 5000, 2.14 / 2.21 ms at N = 1000, but 1.24 / 1.00 ms at N = 100),
-// and it is the only form that runs a partitioned (root-parallel) search without a host step per move.
+// wins where a search is a long chain of moves on one or a few instances with very many rollouts
+// per child (50 tiles: 3.43 / 4.74 ms at N = 5000, but 1.70 / 1.64 ms at N = 1000 and 1.48 / 0.96 ms at
+// N = 100), and it is the only form that runs a partitioned (root-parallel) search without a host
+// step per move.
 static int default_mode(const bp_search* s)
 {
     if (!s->ring_cap) return BP_SEARCH_STEPPED;
     if (s->p.n_ranks > 1) return BP_SEARCH_RESIDENT;
-    return (s->p.n_problems <= 4 && s->max_depth > 32 && s->p.n_chunks >= 16) ? BP_SEARCH_RESIDENT
+    return (s->p.n_problems <= 4 && s->max_depth > 32 && s->p.n_chunks >= 64) ? BP_SEARCH_RESIDENT
                                                                                : BP_SEARCH_STEPPED;
 }
 
