@@ -61,3 +61,17 @@ def test_product_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "from oracle" not in src, f
                 assert "rectpack_oracle" not in src, f
+
+
+def test_search_modes_match_the_header():
+    """bp_search_mode in include/rectpack_b200.h and the names Search.set_mode accepts."""
+    import inspect
+    import re
+    from visapi_b200 import _native
+    header = open(os.path.join(ROOT, "include", "rectpack_b200.h")).read()
+    enum = re.search(r"typedef enum \{([^}]*)\} bp_search_mode;", header).group(1)
+    values = {k.strip(): int(v) for k, v in (item.split("=") for item in enum.split(","))}
+    assert values == {"BP_SEARCH_AUTO": 0, "BP_SEARCH_STEPPED": 1, "BP_SEARCH_RESIDENT": 2, "BP_SEARCH_HYBRID": 3}
+    src = inspect.getsource(_native.Search.set_mode)
+    for name, value in (("auto", 0), ("stepped", 1), ("resident", 2), ("hybrid", 3)):
+        assert '"%s": %d' % (name, value) in src
